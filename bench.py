@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Benchmark of the particle-parallel sampler loop (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+metric  : particle-leapfrog-steps/s == gradient evaluations/s, read from the bit-exact
+          dEdX counter (every leapfrog step does exactly one dEdX on its particles:
+          hmc_state.py:86-91, distributions.py:73-75).
+step    : one launch of the fused sampler kernel = ITERS sampling iterations of the whole
+          particle cloud (sampler.sample_device(ITERS)); samples of every iteration are written.
+value   : device-timed (CUDA events around each step, L2 flushed between steps), state resident in HBM.
+e2e     : the same work through the public API with HOST buffers: the particle state is uploaded
+          from pinned host memory and sample(ITERS) returns a host numpy array, every step.
+N > 1   : one process per GPU (torchrun); particles are independent chains, so each rank owns a
+          contiguous shard of N_PER_GPU particles (weak scaling, no data-path collective); NCCL
+          is used for the barrier, the max-over-ranks time and the int64 counter all-reduce.
+--impl reference : the CPU restatement of the reference (oracle/, numpy float64) on all host cores,
+          on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+# searched hyper-parameters of the reference (mjhmc/search/*/params*.json)
+WORKLOADS = {
+    # configs[1] of BASELINE.json: the configuration the metric is quoted on
+    "roughwell2d_mjhmc": dict(dist="RoughWell", ndims=2, n=1_000_000, sampler="MarkovJumpHMC",
+                              epsilon=3.0, beta=0.012314380146563053, L=25, iters=8,
+                              source="search/MJHMC_rw/params.json"),
+    "roughwell2d_control": dict(dist="RoughWell", ndims=2, n=1_000_000, sampler="ControlHMC",
+                                epsilon=0.6687788963317871, beta=0.5385961532592773, L=22, iters=8,
+                                source="search/control_rw/params_new.json"),
+    "funnel10d_cthmc": dict(dist="Funnel", ndims=10, n=4_000_000, sampler="ContinuousTimeHMC",
+                            epsilon=0.1, beta=0.5, L=10, iters=4, source="search/MJHMC_funnel/config.json midpoints"),
+    # HBM-bound points of the fused leapfrog (one iteration per launch, L = 1)
+    "testgauss2d_control_L1": dict(dist="TestGaussian", ndims=2, n=16_000_000, sampler="ControlHMC",
+                                   epsilon=0.5, beta=0.1, L=1, iters=1, source="HBM roofline point"),
+    "roughwell2d_control_L1": dict(dist="RoughWell", ndims=2, n=16_000_000, sampler="ControlHMC",
+                                   epsilon=0.5, beta=0.1, L=1, iters=1, source="HBM roofline point"),
+}
+DEFAULT_WORKLOAD = "roughwell2d_mjhmc"
+DTYPE = "float64"          # the reference's arithmetic
+METRIC = "particle_leapfrog_steps_per_s"
+UNIT = "particle-leapfrog-steps/s"
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes_per_launch(w, S=8):
+    """DESIGN.md 'Algorithmic traffic': per particle, one launch of `iters` iterations reads X,V,
+    writes X,V, writes one sample column per iteration (+ dwell time of the last iteration for the
+    jump samplers; + FLF cache scalar and flag read and written for MarkovJumpHMC)."""
+    d, it = w["ndims"], w["iters"]
+    per = 4 * d * S + it * d * S
+    if w["sampler"] in ("ContinuousTimeHMC", "MarkovJumpHMC"):
+        per += 8
+    if w["sampler"] == "MarkovJumpHMC":
+        per += 2 * S + 2
+    return per * w["n"]
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on all host cores
+# ----------------------------------------------------------------------------------------------
+def _oracle_energy(w):
+    from oracle import mjhmc_oracle as orc
+    if w["dist"] == "RoughWell":
+        return orc.RoughWellEnergy(100, 4)
+    if w["dist"] == "TestGaussian":
+        return orc.TestGaussianEnergy(1.0)
+    if w["dist"] == "Funnel":
+        return orc.FunnelEnergy(3.0)
+    raise KeyError(w["dist"])
+
+
+def _init_cloud(w, n, seed):
+    rs = np.random.RandomState(seed)
+    d = w["ndims"]
+    if w["dist"] == "RoughWell":
+        X = 100 * rs.randn(d, n)                               # distributions.py:308
+    elif w["dist"] == "Funnel":
+        x0 = rs.normal(scale=3.0, size=(1, n))
+        X = np.vstack((x0, rs.normal(scale=np.exp(x0 / 2.), size=(d - 1, n))))
+    else:
+        X = rs.randn(d, n)
+    return X, rs.randn(d, n)
+
+
+def _oracle_worker(args):
+    w, n, steps, warmup, seed = args
+    from oracle import mjhmc_oracle as orc
+    X, V = _init_cloud(w, n, seed)
+    s = orc.OracleSampler(w["sampler"], _oracle_energy(w), X, V=V, epsilon=w["epsilon"], beta=w["beta"],
+                          num_leapfrog_steps=w["L"], draws=orc.FastNumpyDraws(seed), resample=False)
+    for _ in range(warmup * w["iters"]):
+        s.sampling_iteration()
+    g0 = s.dEdX_count
+    t0 = time.perf_counter()
+    for _ in range(steps * w["iters"]):
+        s.sampling_iteration()
+    return s.dEdX_count - g0, time.perf_counter() - t0
+
+
+def run_reference(w, steps, warmup, n_sample=None, quiet=False):
+    """All host cores: the particle cloud is split over one process per core (chains are independent)."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    n_sample = n_sample or 100_000 * cores
+    per = max(1, n_sample // cores)
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_oracle_worker, [(w, per, steps, warmup, 100 + r) for r in range(cores)])
+    wall = time.perf_counter() - t0
+    grads = sum(r[0] for r in res)
+    t = max(r[1] for r in res)
+    value = grads / t
+    return dict(value=value, unit=UNIT, cores=cores, kind="port",
+                sample="%d particles (%d per core x %d cores), %d steps x %d iterations, numpy float64 oracle port "
+                       "with vectorised draws; wall incl. process start %.1fs" % (per * cores, per, cores, steps, w["iters"], wall),
+                ms_per_step=1e3 * t / max(steps, 1), n_particles=per * cores)
+
+
+# ----------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:   # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:   # noqa: BLE001
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, reasons = [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                out["sm_max_mhz"] = float(parts[1])
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.tmp.name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def make_sampler(w, rank, dtype=DTYPE, seed=2024):
+    from mjhmc_b200.misc import distributions as D
+    from mjhmc_b200.samplers import markov_jump_hmc as S
+    n, d = w["n"], w["ndims"]
+    if w["dist"] == "RoughWell":
+        dist = D.RoughWell(ndims=d, nbatch=n)
+    elif w["dist"] == "TestGaussian":
+        dist = D.TestGaussian(ndims=d, nbatch=n)
+    elif w["dist"] == "Funnel":
+        dist = D.Funnel(scale=3.0, ndims=d, nbatch=n)
+    else:
+        raise KeyError(w["dist"])
+    X0, V0 = _init_cloud(w, n, 1000 + rank)
+    dist.gen_init_X = lambda: setattr(dist, "Xinit", X0)
+    kw = dict(resample=False) if w["sampler"] in ("ContinuousTimeHMC", "MarkovJumpHMC") else {}
+    s = getattr(S, w["sampler"])(distribution=dist, epsilon=w["epsilon"], beta=w["beta"], num_leapfrog_steps=w["L"],
+                                 V=V0, dtype=dtype, seed=seed, particle_offset=rank * n, **kw)
+    return s, dist, X0, V0
+
+
+def run_b200(args, w):
+    import torch
+    import torch.distributed as dist_pkg
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist_pkg.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist_pkg.barrier()
+        torch.cuda.synchronize()
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = run_reference(w, steps=2, warmup=1)
+
+    sampler, dist, X0, V0 = make_sampler(w, rank)
+    eng = sampler._engine
+    iters = w["iters"]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
+
+    def step():
+        return sampler.sample_device(iters)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    g0, launches0 = dist.dEdX_count, eng.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(float(k))                 # evict the state from L2 between timed steps
+        ev[k][0].record()
+        out = step()
+        ev[k][1].record()
+        del out
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clk = clocks.stop() if rank == 0 else None
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    grads = dist.dEdX_count - g0
+    launches = eng.launches - launches0
+    tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+    gg = torch.tensor([grads, launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist_pkg.all_reduce(tt, op=dist_pkg.ReduceOp.MAX)
+        dist_pkg.all_reduce(gg, op=dist_pkg.ReduceOp.SUM)          # counters: the only cross-GPU reduction
+    ms_max = float(tt.item())
+    grads_all, launches_all = int(gg[0].item()), int(gg[1].item())
+    value = grads_all / (ms_max * 1e-3)
+
+    # ---- e2e: host buffers in, host samples out, through the public API, every step
+    from mjhmc_b200.samplers.hmc_state import HMCState
+    Xh = torch.as_tensor(X0).pin_memory().numpy()
+    Vh = torch.as_tensor(V0).pin_memory().numpy()
+    e2e_steps = max(1, min(args.steps, 5))
+    barrier()
+    g1 = dist.dEdX_count
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        st = HMCState.__new__(HMCState)
+        st.parent, st.X, st.V, st.nbatch = sampler, Xh, Vh, Xh.shape[1]
+        st.cache_active = np.zeros(st.nbatch, dtype=bool)
+        st.H_cache = np.zeros(st.nbatch)
+        sampler.state = st                                   # H2D at the next launch
+        res = sampler.sample(iters)                          # D2H of (ndims, iters * n)
+    barrier()
+    e2e_t = time.perf_counter() - t0
+    ee = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
+    ge = torch.tensor([dist.dEdX_count - g1], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist_pkg.all_reduce(ee, op=dist_pkg.ReduceOp.MAX)
+        dist_pkg.all_reduce(ge, op=dist_pkg.ReduceOp.SUM)
+    e2e_value = int(ge.item()) / float(ee.item())
+    S = 8
+    h2d = 2 * w["ndims"] * w["n"] * S + w["n"] * (S + 1)
+    d2h = res.nbytes
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg = algorithmic_bytes_per_launch(w)
+        launch_ms = ms_max / args.steps
+        achieved = alg / (launch_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %s %d-d, %d particles per GPU, %s eps=%g beta=%g L=%d (%s); %d sampling "
+                                   "iterations per step in one fused launch" % (
+                                       args.workload, w["dist"], w["ndims"], w["n"], w["sampler"], w["epsilon"], w["beta"],
+                                       w["L"], w["source"], iters),
+                       "particles_per_gpu": w["n"], "iterations_per_step": iters,
+                       "l2": "flushed with a 256 MB fill between timed steps", "rng": "philox4x32-10",
+                       "parallelism": "particle shards, dp%d" % world},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "fused_sample_kernel",
+                         "algorithmic_bytes_per_launch": alg, "launch_ms": launch_ms,
+                         "note": "L=%d leapfrog steps of fp64 sin() per sample: the kernel is FP64-issue bound, "
+                                 "see DESIGN.md" % w["L"] if w["L"] > 4 else "HBM-bound point"},
+            "cpu_baseline": cpu_baseline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": launches_all,
+            "clocks": clk,
+            "wall_s_timed_region": t_wall,
+            "grad_evals": grads_all,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist_pkg.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    w = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        steps = max(1, min(args.steps, 3))
+        warm = min(args.warmup, 1)
+        r = run_reference(w, steps=steps, warmup=warm)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %s %d-d, %s eps=%g beta=%g L=%d; bounded sample of %d particles; %d sampling "
+                                   "iterations per step" % (args.workload, w["dist"], w["ndims"], w["sampler"],
+                                                            w["epsilon"], w["beta"], w["L"], r["n_particles"], w["iters"])},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return
+    run_b200(args, w)
+
+
+if __name__ == "__main__":
+    main()

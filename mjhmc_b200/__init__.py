@@ -1,0 +1,26 @@
+"""mjhmc_b200 -- B200-native implementation of MJHMC's particle-parallel sampler loop.
+
+Drop-in for the reference's ``mjhmc.samplers.markov_jump_hmc`` and ``mjhmc.misc.distributions``
+(same class names, arguments and attributes); see INTEGRATION.md.  ``install_alias()`` registers
+the package under the reference's module names so ``from mjhmc.samplers.markov_jump_hmc import
+MarkovJumpHMC`` resolves to this implementation.
+"""
+import sys
+
+__version__ = "0.1.0"
+
+
+def install_alias(name="mjhmc"):
+    from . import misc, samplers
+    from .misc import distributions, utils
+    from .samplers import hmc_state, markov_jump_hmc
+    pkg = sys.modules[__name__]
+    sys.modules[name] = pkg
+    sys.modules[name + ".misc"] = misc
+    sys.modules[name + ".misc.distributions"] = distributions
+    sys.modules[name + ".misc.tf_distributions"] = distributions      # Funnel's reference location
+    sys.modules[name + ".misc.utils"] = utils
+    sys.modules[name + ".samplers"] = samplers
+    sys.modules[name + ".samplers.markov_jump_hmc"] = markov_jump_hmc
+    sys.modules[name + ".samplers.hmc_state"] = hmc_state
+    return pkg

@@ -1,0 +1,196 @@
+// K6 dwell-time resampler and K7 autocorrelation.
+//   resample : ContinuousTimeHMC.sample, samplers/markov_jump_hmc.py:321-328
+//   autocorr : fft_autocor, misc/autocor.py:37-49 (as a direct circular product)
+#include "common.cuh"
+#include "analysis.h"
+
+namespace mjhmc {
+
+// ------------------------------------------------------------------ inclusive scan (double)
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;                     // per thread
+constexpr int kScanChunk = kScanThreads * kScanItems;
+
+__device__ __forceinline__ double block_exclusive_scan(double v, double* sm, double& total) {
+    // Hillis-Steele over warp totals; returns the exclusive prefix of v within the block.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) sm[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        double w = lane < (kScanThreads / 32) ? sm[lane] : 0.0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
+        }
+        if (lane < (kScanThreads / 32)) sm[lane] = w;
+    }
+    __syncthreads();
+    const double warp_off = warp ? sm[warp - 1] : 0.0;
+    total = sm[kScanThreads / 32 - 1];
+    __syncthreads();
+    return warp_off + inc - v;
+}
+
+// phase 1: chunk sums
+__global__ void __launch_bounds__(kScanThreads) scan_chunk_sums(const double* __restrict__ in, long long m,
+                                                                double* __restrict__ sums) {
+    __shared__ double sm[32];
+    const long long base = (long long)blockIdx.x * kScanChunk + (long long)threadIdx.x * kScanItems;
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) if (base + j < m) s += in[base + j];
+    double total;
+    block_exclusive_scan(s, sm, total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+// phase 2: in-place inclusive->exclusive scan of the chunk sums by one block
+__global__ void __launch_bounds__(kScanThreads) scan_sums_inplace(double* __restrict__ sums, long long nchunks) {
+    __shared__ double sm[32];
+    __shared__ double carry_s;
+    if (threadIdx.x == 0) carry_s = 0.0;
+    __syncthreads();
+    for (long long base = 0; base < nchunks; base += kScanThreads) {
+        const long long idx = base + threadIdx.x;
+        const double v = idx < nchunks ? sums[idx] : 0.0;
+        double total;
+        const double ex = block_exclusive_scan(v, sm, total);
+        const double carry = carry_s;
+        if (idx < nchunks) sums[idx] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+}
+
+// phase 3: scan inside each chunk + chunk offset
+__global__ void __launch_bounds__(kScanThreads) scan_chunks(const double* __restrict__ in, long long m,
+                                                            const double* __restrict__ offsets,
+                                                            double* __restrict__ out) {
+    __shared__ double sm[32];
+    const long long base = (long long)blockIdx.x * kScanChunk + (long long)threadIdx.x * kScanItems;
+    double loc[kScanItems];
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) { loc[j] = base + j < m ? in[base + j] : 0.0; s += loc[j]; }
+    double total;
+    double run = offsets[blockIdx.x] + block_exclusive_scan(s, sm, total);
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) { run += loc[j]; if (base + j < m) out[base + j] = run; }
+}
+
+// idx[j] = first i with cumul[i] > r[j]  (np.searchsorted(cumul, r, 'right')), then gather columns
+template <typename T>
+__global__ void __launch_bounds__(256) search_gather_kernel(const double* __restrict__ cumul, long long m,
+                                                            const double* __restrict__ r, long long m_out, int d,
+                                                            const T* __restrict__ samples, long long ld_in,
+                                                            T* __restrict__ out, long long ld_out,
+                                                            long long* __restrict__ idx_out) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m_out) return;
+    const double rv = r[j];
+    long long lo = 0, hi = m;                    // first index with cumul > rv
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (cumul[mid] > rv) hi = mid; else lo = mid + 1;
+    }
+    if (idx_out) idx_out[j] = lo;
+    const long long src = lo < m ? lo : m - 1;   // the reference raises IndexError past the end
+    for (int k = 0; k < d; ++k) out[k * ld_out + j] = samples[k * ld_in + src];
+}
+
+long long resample_scratch_bytes(long long m) {
+    const long long nchunks = (m + kScanChunk - 1) / kScanChunk;
+    return (long long)sizeof(double) * (m + nchunks + 8);
+}
+
+cudaError_t launch_resample(int dtype, int d, const double* dwell, long long m, const double* r, long long m_out,
+                            const void* samples, long long ld_in, void* out, long long ld_out, long long* idx_out,
+                            void* scratch, cudaStream_t s) {
+    if (m == 0 || m_out == 0) return cudaSuccess;
+    const long long nchunks = (m + kScanChunk - 1) / kScanChunk;
+    double* cumul = (double*)scratch;
+    double* sums = cumul + m;
+    scan_chunk_sums<<<(unsigned)nchunks, kScanThreads, 0, s>>>(dwell, m, sums);
+    scan_sums_inplace<<<1, kScanThreads, 0, s>>>(sums, nchunks);
+    scan_chunks<<<(unsigned)nchunks, kScanThreads, 0, s>>>(dwell, m, sums, cumul);
+    const unsigned grid = (unsigned)((m_out + 255) / 256);
+    if (dtype == MJHMC_F64)
+        search_gather_kernel<double><<<grid, 256, 0, s>>>(cumul, m, r, m_out, d, (const double*)samples, ld_in,
+                                                          (double*)out, ld_out, idx_out);
+    else
+        search_gather_kernel<float><<<grid, 256, 0, s>>>(cumul, m, r, m_out, d, (const float*)samples, ld_in,
+                                                         (float*)out, ld_out, idx_out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ autocorrelation
+// Block = (one dim k, a tile of kAcP particles).  The T x kAcP series tile sits in shared
+// memory; thread (p, g) accumulates lags tau = g, g+kAcG, ... for particle p; partial sums
+// over the particles of the tile are combined by a shared-memory reduction and added to ac[].
+constexpr int kAcP = 16;
+constexpr int kAcG = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(kAcP * kAcG) autocorr_kernel(const T* __restrict__ samples, long long stride_k,
+                                                               long long stride_it, long long n, int Tn, int n_lags,
+                                                               double* __restrict__ ac) {
+    extern __shared__ double tile[];              // [Tn][kAcP]
+    __shared__ double red[kAcG][kAcP + 1];
+    const int p = threadIdx.x % kAcP, g = threadIdx.x / kAcP;
+    const long long i0 = (long long)blockIdx.x * kAcP;
+    const T* base = samples + (long long)blockIdx.y * stride_k;
+    for (int t = g; t < Tn; t += kAcG) {
+        const long long i = i0 + p;
+        tile[t * kAcP + p] = i < n ? (double)base[(long long)t * stride_it + i] : 0.0;
+    }
+    __syncthreads();
+    for (int tau0 = 0; tau0 < n_lags; tau0 += kAcG) {
+        const int tau = tau0 + g;
+        double acc = 0.0;
+        if (tau < n_lags) {
+            int t2 = tau % Tn;
+            for (int t = 0; t < Tn; ++t) {
+                acc += tile[t * kAcP + p] * tile[t2 * kAcP + p];
+                t2 = t2 + 1 == Tn ? 0 : t2 + 1;
+            }
+        }
+        red[g][p] = acc;
+        __syncthreads();
+        if (p == 0 && tau < n_lags) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < kAcP; ++q) s += red[g][q];
+            atomicAdd(ac + tau, s);
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_autocorr(int dtype, int d, const void* samples, long long stride_k, long long stride_it,
+                            long long n, int Tn, int n_lags, double* ac, cudaStream_t s) {
+    if (n == 0 || Tn == 0 || n_lags == 0) return cudaSuccess;
+    const size_t smem = sizeof(double) * (size_t)Tn * kAcP;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    dim3 grid((unsigned)((n + kAcP - 1) / kAcP), (unsigned)d);
+    cudaError_t e;
+    if (dtype == MJHMC_F64) {
+        e = cudaFuncSetAttribute(autocorr_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        autocorr_kernel<double><<<grid, kAcP * kAcG, smem, s>>>((const double*)samples, stride_k, stride_it, n, Tn, n_lags, ac);
+    } else {
+        e = cudaFuncSetAttribute(autocorr_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        autocorr_kernel<float><<<grid, kAcP * kAcG, smem, s>>>((const float*)samples, stride_k, stride_it, n, Tn, n_lags, ac);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace mjhmc

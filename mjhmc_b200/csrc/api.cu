@@ -1,0 +1,277 @@
+// C ABI of libmjhmc_b200.so (include/mjhmc_b200.h): argument checking, parameter
+// packing and kernel dispatch.  No torch types, no hidden allocation, no CPU path.
+#include <string>
+#include <cstdio>
+#include <cstring>
+#include <climits>
+#include "fused_elementwise.cuh"
+#include "unfused.h"
+#include "analysis.h"
+#include "dense.h"
+
+namespace mjhmc {
+fused_launch_fn find_fused_f64_g0(int, int); fused_launch_fn find_fused_f64_g1(int, int);
+fused_launch_fn find_fused_f64_g2(int, int); fused_launch_fn find_fused_f64_g3(int, int);
+fused_launch_fn find_fused_f32_g0(int, int); fused_launch_fn find_fused_f32_g1(int, int);
+fused_launch_fn find_fused_f32_g2(int, int); fused_launch_fn find_fused_f32_g3(int, int);
+
+static thread_local std::string g_err;
+static int fail(const char* fmt, const char* a = "") {
+    char buf[512];
+    snprintf(buf, sizeof buf, fmt, a);
+    g_err = buf;
+    return -1;
+}
+static int check(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return -2;
+}
+
+static fused_launch_fn find_fused(int dtype, int kind, int D) {
+    fused_launch_fn f = nullptr;
+    if (dtype == MJHMC_F64) {
+        if (!f) f = find_fused_f64_g0(kind, D);
+        if (!f) f = find_fused_f64_g1(kind, D);
+        if (!f) f = find_fused_f64_g2(kind, D);
+        if (!f) f = find_fused_f64_g3(kind, D);
+    } else {
+        if (!f) f = find_fused_f32_g0(kind, D);
+        if (!f) f = find_fused_f32_g1(kind, D);
+        if (!f) f = find_fused_f32_g2(kind, D);
+        if (!f) f = find_fused_f32_g3(kind, D);
+    }
+    return f;
+}
+
+static bool is_elementwise(int kind) { return kind >= MJHMC_DIST_TEST_GAUSSIAN && kind <= MJHMC_DIST_FUNNEL_LITERAL; }
+static bool is_dense(int kind) { return kind == MJHMC_DIST_DENSE_GAUSSIAN || kind == MJHMC_DIST_PRODUCT_OF_T; }
+
+static int fill_hp(LaunchParams& p, const mjhmc_hp* hp) {
+    if (hp->sampler < MJHMC_SAMPLER_DISCRETE || hp->sampler > MJHMC_SAMPLER_MARKOV_JUMP) return fail("bad sampler kind");
+    if (hp->num_leapfrog_steps < 0) return fail("num_leapfrog_steps < 0");
+    if (!(hp->beta >= 0.0 && hp->beta <= 1.0)) return fail("beta must be in [0, 1]");
+    if (hp->sampler != MJHMC_SAMPLER_DISCRETE && !(hp->p_r >= 0.0 && hp->p_r < INFINITY))
+        return fail("p_r must be a finite non-negative rate (Infinite rate)");
+    p.sampler = hp->sampler;
+    p.L = hp->num_leapfrog_steps;
+    p.eps = hp->epsilon;
+    p.p_flip = hp->p_flip;
+    p.p_r = hp->p_r;
+    p.r_keep = sqrt(1.0 - hp->beta);
+    p.r_mix = sqrt(hp->beta);
+    return 0;
+}
+
+static int fill_rng(LaunchParams& p, const mjhmc_rng* rng) {
+    p.rng_mode = rng->mode;
+    p.seed = rng->seed;
+    p.attempt0 = rng->attempt0;
+    p.particle0 = rng->particle0;
+    p.Z = rng->Z; p.U = rng->U; p.U0 = rng->U0; p.inj_ld = rng->inj_ld;
+    if (rng->mode == MJHMC_RNG_INJECT) {
+        if (!rng->U) return fail("INJECT mode needs U");
+        if (rng->inj_ld <= 0) return fail("INJECT mode needs inj_ld");
+    } else if (rng->mode != MJHMC_RNG_PHILOX) {
+        return fail("bad rng mode");
+    }
+    return 0;
+}
+
+static void fill_outputs(LaunchParams& p, const mjhmc_outputs* o) {
+    p.samples = o->samples; p.s_stride_k = o->stride_k; p.s_stride_it = o->stride_it;
+    p.dwell = o->dwell; p.dwell_last = o->dwell_last; p.choice = o->choice;
+    p.counters = (unsigned long long*)o->counters;
+}
+
+static int fill_dist(LaunchParams& p, const mjhmc_dist* dist) {
+    p.d = dist->ndims;
+    p.nbasis = dist->nbasis;
+    for (int k = 0; k < 4; ++k) p.dp[k] = dist->p[k];
+    p.a0 = dist->a0; p.a1 = dist->a1; p.a2 = dist->a2;
+    return 0;
+}
+
+static DistParams dist_params(const mjhmc_dist* dist) {
+    DistParams dp;
+    dp.kind = dist->kind; dp.d = dist->ndims; dp.nbasis = dist->nbasis;
+    for (int k = 0; k < 4; ++k) dp.p[k] = dist->p[k];
+    dp.a0 = dist->a0; dp.a1 = dist->a1; dp.a2 = dist->a2;
+    return dp;
+}
+
+static int check_dist(const mjhmc_dist* dist) {
+    if (!dist) return fail("dist is NULL");
+    if (dist->dtype != MJHMC_F32 && dist->dtype != MJHMC_F64) return fail("bad dtype");
+    if (dist->ndims <= 0) return fail("ndims must be positive");
+    if (dist->kind < MJHMC_DIST_TEST_GAUSSIAN || dist->kind > MJHMC_DIST_PRODUCT_OF_T) return fail("bad distribution kind");
+    if ((dist->kind == MJHMC_DIST_DIAG_GAUSSIAN || is_dense(dist->kind)) && !dist->a0) return fail("distribution needs a0");
+    if (dist->kind == MJHMC_DIST_PRODUCT_OF_T && (!dist->a1 || !dist->a2 || dist->nbasis <= 0)) return fail("ProductOfT needs a1, a2, nbasis");
+    return 0;
+}
+
+}  // namespace mjhmc
+
+using namespace mjhmc;
+
+extern "C" {
+
+const char* mjhmc_last_error(void) { return g_err.c_str(); }
+int mjhmc_abi_version(void) { return MJHMC_ABI_VERSION; }
+
+int mjhmc_fused_supported(const mjhmc_dist* dist) {
+    if (check_dist(dist)) return 0;
+    if (is_elementwise(dist->kind)) {
+        const int D = fused_template_dim(dist->ndims);
+        return D && find_fused(dist->dtype, dist->kind, D) ? 1 : 0;
+    }
+    return dense_supported(dist->dtype, dist->kind, dist->ndims, dist->nbasis) ? 1 : 0;
+}
+
+int mjhmc_sample_fused(const mjhmc_dist* dist, const mjhmc_hp* hp, const mjhmc_rng* rng,
+                       const mjhmc_state* in, const mjhmc_state* out, int32_t n_iter,
+                       const mjhmc_outputs* o, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (check_dist(dist)) return -1;
+    if (!hp || !rng || !in || !out || !o) return fail("NULL argument");
+    if (!o->counters) return fail("outputs.counters is required");
+    if (n_iter < 0) return fail("n_iter < 0");
+    if (in->n != out->n || in->ld != out->ld) return fail("in/out state shapes differ");
+    if (in->n < 0 || in->ld < in->n) return fail("bad n / ld");
+    if (!in->X || !in->V || !out->X || !out->V) { if (in->n) return fail("state X/V is NULL"); }
+    LaunchParams p;
+    memset(&p, 0, sizeof p);
+    if (fill_hp(p, hp)) return -1;
+    if (fill_rng(p, rng)) return -1;
+    if (rng->mode == MJHMC_RNG_INJECT) {
+        const bool needs_z = hp->sampler == MJHMC_SAMPLER_DISCRETE ? hp->p_r > 0.0 : hp->p_r != 0.0;
+        if (needs_z && !rng->Z) return fail("INJECT mode needs Z");
+        if (hp->sampler == MJHMC_SAMPLER_DISCRETE && !rng->U0) return fail("INJECT mode needs U0 for discrete samplers");
+    }
+    if (hp->sampler == MJHMC_SAMPLER_MARKOV_JUMP && in->n &&
+        (!in->H_cache || !in->cache_active || !out->H_cache || !out->cache_active))
+        return fail("MarkovJumpHMC needs H_cache and cache_active");
+    fill_outputs(p, o);
+    if (int rc = fill_dist(p, dist)) return rc;
+    p.Xin = in->X; p.Vin = in->V; p.Xout = out->X; p.Vout = out->V;
+    p.Hc_in = in->H_cache; p.Hc_out = out->H_cache; p.ca_in = in->cache_active; p.ca_out = out->cache_active;
+    p.n = in->n; p.ld = in->ld; p.n_iter = n_iter;
+    if (p.n == 0) return 0;
+    if (is_elementwise(dist->kind)) {
+        const int D = fused_template_dim(dist->ndims);
+        fused_launch_fn fn = D ? find_fused(dist->dtype, dist->kind, D) : nullptr;
+        if (!fn) return fail("no fused kernel for this distribution / ndims (use the unfused path)");
+        return check(fn(p, stream), "fused_sample_kernel");
+    }
+    if (!dense_supported(dist->dtype, dist->kind, dist->ndims, dist->nbasis))
+        return fail("no fused dense kernel for this distribution / shape (use the unfused path)");
+    return check(launch_dense(dist->dtype, dist->kind, p, stream), "dense_sample_kernel");
+}
+
+int mjhmc_energy(const mjhmc_dist* dist, const void* X, int64_t n, int64_t ld, void* E, void* stream) {
+    if (check_dist(dist)) return -1;
+    if (n < 0 || ld < n) return fail("bad n / ld");
+    if (n && (!X || !E)) return fail("NULL argument");
+    return check(launch_energy(dist->dtype, dist_params(dist), X, n, ld, E, (cudaStream_t)stream), "energy_kernel");
+}
+
+int mjhmc_gradient(const mjhmc_dist* dist, const void* X, int64_t n, int64_t ld, void* G, void* stream) {
+    if (check_dist(dist)) return -1;
+    if (n < 0 || ld < n) return fail("bad n / ld");
+    if (n && (!X || !G)) return fail("NULL argument");
+    return check(launch_gradient(dist->dtype, dist_params(dist), X, n, ld, G, (cudaStream_t)stream), "gradient_kernel");
+}
+
+int mjhmc_kinetic(int32_t dtype, int32_t ndims, const void* V, int64_t n, int64_t ld, void* EV, void* stream) {
+    if (dtype != MJHMC_F32 && dtype != MJHMC_F64) return fail("bad dtype");
+    if (n < 0 || ld < n || ndims <= 0) return fail("bad n / ld / ndims");
+    if (n && (!V || !EV)) return fail("NULL argument");
+    return check(launch_kinetic(dtype, ndims, V, n, ld, EV, (cudaStream_t)stream), "kinetic_kernel");
+}
+
+int mjhmc_kick_drift(int32_t dtype, int32_t ndims, void* X, void* V, const void* G, int64_t n, int64_t ld,
+                     double epsilon, void* stream) {
+    if (dtype != MJHMC_F32 && dtype != MJHMC_F64) return fail("bad dtype");
+    if (n < 0 || ld < n || ndims <= 0) return fail("bad n / ld / ndims");
+    if (n && (!X || !V || !G)) return fail("NULL argument");
+    return check(launch_kick(dtype, ndims, X, V, G, n, ld, epsilon, true, (cudaStream_t)stream), "kick_drift");
+}
+
+int mjhmc_kick(int32_t dtype, int32_t ndims, void* V, const void* G, int64_t n, int64_t ld, double epsilon,
+               void* stream) {
+    if (dtype != MJHMC_F32 && dtype != MJHMC_F64) return fail("bad dtype");
+    if (n < 0 || ld < n || ndims <= 0) return fail("bad n / ld / ndims");
+    if (n && (!V || !G)) return fail("NULL argument");
+    return check(launch_kick(dtype, ndims, nullptr, V, G, n, ld, epsilon, false, (cudaStream_t)stream), "kick");
+}
+
+int mjhmc_transition(int32_t dtype, int32_t ndims, const mjhmc_hp* hp, const mjhmc_rng* rng, int64_t n, int64_t ld,
+                     const mjhmc_full_state* cur, const mjhmc_full_state* prop, const void* H_flf, void* H_cache,
+                     uint8_t* cache_active, const mjhmc_outputs* o, void* stream) {
+    if (dtype != MJHMC_F32 && dtype != MJHMC_F64) return fail("bad dtype");
+    if (!hp || !rng || !cur || !prop || !o) return fail("NULL argument");
+    if (!o->counters) return fail("outputs.counters is required");
+    if (n < 0 || ld < n || ndims <= 0) return fail("bad n / ld / ndims");
+    LaunchParams p;
+    memset(&p, 0, sizeof p);
+    if (fill_hp(p, hp)) return -1;
+    if (fill_rng(p, rng)) return -1;
+    fill_outputs(p, o);
+    p.d = ndims; p.n = n; p.ld = ld; p.n_iter = 1;
+    p.Hc_out = H_cache; p.ca_out = cache_active;
+    if (hp->sampler == MJHMC_SAMPLER_MARKOV_JUMP && n && (!H_flf || !H_cache || !cache_active))
+        return fail("MarkovJumpHMC transition needs H_flf, H_cache, cache_active");
+    FullPtrs c{cur->X, cur->V, cur->G, cur->EX, cur->EV};
+    FullPtrs q{prop->X, prop->V, prop->G, prop->EX, prop->EV};
+    if (n && (!c.X || !c.V || !c.G || !c.EX || !c.EV || !q.X || !q.V || !q.G || !q.EX || !q.EV))
+        return fail("state arrays must not be NULL");
+    return check(launch_transition(dtype, p, c, q, H_flf, (cudaStream_t)stream), "transition_kernel");
+}
+
+int mjhmc_counters_reset(int64_t* counters, void* stream_) {
+    if (!counters) return fail("NULL argument");
+    int64_t h[MJHMC_COUNTER_STRIPES][MJHMC_N_COUNTERS];
+    memset(h, 0, sizeof h);
+    for (int s = 0; s < MJHMC_COUNTER_STRIPES; ++s) h[s][MJHMC_CNT_FAIL] = INT64_MAX;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (check(cudaMemcpyAsync(counters, h, sizeof h, cudaMemcpyHostToDevice, stream), "counters_reset")) return -2;
+    return check(cudaStreamSynchronize(stream), "counters_reset");
+}
+
+int mjhmc_counters_read(const int64_t* counters, int64_t* out_host, void* stream_) {
+    if (!counters || !out_host) return fail("NULL argument");
+    int64_t h[MJHMC_COUNTER_STRIPES][MJHMC_N_COUNTERS];
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (check(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, stream), "counters_read")) return -2;
+    if (check(cudaStreamSynchronize(stream), "counters_read")) return -2;
+    for (int c = 0; c < MJHMC_N_COUNTERS; ++c) out_host[c] = 0;
+    out_host[MJHMC_CNT_FAIL] = INT64_MAX;
+    for (int s = 0; s < MJHMC_COUNTER_STRIPES; ++s)
+        for (int c = 0; c < MJHMC_N_COUNTERS; ++c) {
+            if (c == MJHMC_CNT_FAIL) { if (h[s][c] < out_host[c]) out_host[c] = h[s][c]; }
+            else out_host[c] += h[s][c];
+        }
+    return 0;
+}
+
+int64_t mjhmc_resample_scratch_bytes(int64_t m) { return m < 0 ? -1 : resample_scratch_bytes(m); }
+
+int mjhmc_resample(int32_t dtype, int32_t ndims, const double* dwell, int64_t m, const double* r, int64_t m_out,
+                   const void* samples, int64_t ld_in, void* out, int64_t ld_out, int64_t* idx_out, void* scratch,
+                   void* stream) {
+    if (dtype != MJHMC_F32 && dtype != MJHMC_F64) return fail("bad dtype");
+    if (m < 0 || m_out < 0 || ndims <= 0 || ld_in < m || ld_out < m_out) return fail("bad sizes");
+    if (m && m_out && (!dwell || !r || !samples || !out || !scratch)) return fail("NULL argument");
+    return check(launch_resample(dtype, ndims, dwell, m, r, m_out, samples, ld_in, out, ld_out,
+                                 (long long*)idx_out, scratch, (cudaStream_t)stream), "resample");
+}
+
+int mjhmc_autocorr(int32_t dtype, int32_t ndims, const void* samples, int64_t stride_k, int64_t stride_it, int64_t n,
+                   int32_t T, int32_t n_lags, double* ac, void* stream) {
+    if (dtype != MJHMC_F32 && dtype != MJHMC_F64) return fail("bad dtype");
+    if (n < 0 || T < 0 || n_lags < 0 || ndims <= 0) return fail("bad sizes");
+    if (n && T && n_lags && (!samples || !ac)) return fail("NULL argument");
+    return check(launch_autocorr(dtype, ndims, samples, stride_k, stride_it, n, T, n_lags, ac, (cudaStream_t)stream), "autocorr");
+}
+
+}  // extern "C"

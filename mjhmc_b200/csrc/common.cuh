@@ -1,0 +1,218 @@
+// Shared device helpers: Philox4x32-10 stream, draw access, reductions.
+// sm_100a only.  Reference call sites replaced: np.random.* in
+// samplers/hmc_state.py:126, samplers/markov_jump_hmc.py:125,132,138, misc/utils.py:42.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/mjhmc_b200.h"
+
+namespace mjhmc {
+
+constexpr int kMaxRegDims = 16;          // largest ndims with a register-resident fused kernel
+
+// Kernel-side view of one launch (passed by value as a __grid_constant__ parameter).
+struct LaunchParams {
+    // state
+    const void* Xin; const void* Vin; void* Xout; void* Vout;
+    const void* Hc_in; void* Hc_out; const uint8_t* ca_in; uint8_t* ca_out;
+    long long n, ld;
+    // outputs
+    void* samples; long long s_stride_k, s_stride_it;
+    double* dwell; double* dwell_last; uint8_t* choice;
+    unsigned long long* counters;
+    // hyper-parameters
+    int sampler, L, n_iter, d;
+    double eps, p_flip, p_r, r_keep, r_mix;   // r_keep = sqrt(1-beta), r_mix = sqrt(beta)
+    // rng
+    int rng_mode;
+    unsigned long long seed, attempt0, particle0;
+    const double* Z; const double* U; const double* U0; long long inj_ld;
+    // distribution
+    double dp[4];
+    const void* a0; const void* a1; const void* a2; int nbasis;
+};
+
+// ---------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += W0; k.y += W1;
+    }
+    return c;
+}
+
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
+    // numpy legacy double: (a>>5, b>>6) -> [0,1)
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ uint4 philox_at(unsigned long long seed, unsigned long long particle,
+                                           unsigned long long attempt, uint32_t slot) {
+    return philox4x32_10(make_uint4((uint32_t)particle, (uint32_t)(particle >> 32), (uint32_t)attempt, slot),
+                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+
+// The three per-particle uniforms of one attempt (slots: see oracle/philox.py).
+struct Uniform3 { double u0, u1, u2; };
+
+__device__ __forceinline__ Uniform3 draw_uniforms(const LaunchParams& p, long long i, unsigned long long attempt,
+                                                  bool need_u2) {
+    Uniform3 r;
+    if (p.rng_mode == MJHMC_RNG_INJECT) {
+        const double* base = p.U + (attempt * 3ull) * (unsigned long long)p.inj_ld + p.particle0 + i;
+        r.u0 = base[0];
+        r.u1 = base[p.inj_ld];
+        r.u2 = need_u2 ? base[2 * p.inj_ld] : 0.0;
+    } else {
+        const unsigned long long g = p.particle0 + (unsigned long long)i;
+        const uint4 w = philox_at(p.seed, g, attempt, 0u);
+        r.u0 = u53(w.x, w.y);
+        r.u1 = u53(w.z, w.w);
+        if (need_u2) {
+            const uint4 w1 = philox_at(p.seed, g, attempt, 1u);
+            r.u2 = u53(w1.x, w1.y);
+        } else {
+            r.u2 = 0.0;
+        }
+    }
+    return r;
+}
+
+__device__ __forceinline__ double draw_coin(const LaunchParams& p, unsigned long long attempt) {
+    if (p.rng_mode == MJHMC_RNG_INJECT) return p.U0[attempt];
+    const uint4 w = philox_at(p.seed, 0xFFFFFFFFFFFFFFFFull, attempt, 0u);
+    return u53(w.x, w.y);
+}
+
+// Box-Muller pair j of particle i, attempt a: normals 2j and 2j+1 (z1 unused when 2j+1 == d).
+__device__ __forceinline__ void normal_pair(const LaunchParams& p, long long i, unsigned long long attempt,
+                                            int j, int d, double& z0, double& z1) {
+    if (p.rng_mode == MJHMC_RNG_INJECT) {
+        const double* base = p.Z + (attempt * (unsigned long long)d + 2ull * j) * (unsigned long long)p.inj_ld
+                             + p.particle0 + i;
+        z0 = base[0];
+        z1 = (2 * j + 1 < d) ? base[p.inj_ld] : 0.0;
+    } else {
+        const uint4 w = philox_at(p.seed, p.particle0 + (unsigned long long)i, attempt, 2u + (uint32_t)j);
+        const double u1 = u53(w.x, w.y), u2 = u53(w.z, w.w);
+        const double r = sqrt(-2.0 * log(1.0 - u1));
+        double s, c;
+        sincospi(2.0 * u2, &s, &c);
+        z0 = r * c;
+        z1 = r * s;
+    }
+}
+
+// Standard normals z[0..d) for particle i, attempt a (rows >= d are zero padding).
+template <typename T, int D>
+__device__ __forceinline__ void draw_normals(const LaunchParams& p, long long i, unsigned long long attempt,
+                                             int d, T (&z)[D]) {
+#pragma unroll
+    for (int j = 0; j < (D + 1) / 2; ++j) {
+        double z0 = 0.0, z1 = 0.0;
+        if (2 * j < d) normal_pair(p, i, attempt, j, d, z0, z1);
+        z[2 * j] = (T)z0;
+        if (2 * j + 1 < D) z[2 * j + 1] = (2 * j + 1 < d) ? (T)z1 : (T)0;
+    }
+}
+
+// np.random.exponential(scale = 1/rate) == (1/rate) * -log(1 - u); zero rate -> inf (utils.py:38-42)
+__device__ __forceinline__ double exp_draw(double rate, double u) {
+    return rate == 0.0 ? INFINITY : (1.0 / rate) * (-log(1.0 - u));
+}
+
+// transition rate exp(H - H')**.5 (markov_jump_hmc.py:341-347)
+__device__ __forceinline__ double jump_rate(double ediff) { return sqrt(exp(ediff)); }
+
+// ---------------------------------------------------------------- transitions
+// The operator choice of one particle for one attempt.  `fail` = a non-finite rate
+// (misc/utils.py:41-48), which the host turns into the batch-wide back-off / ValueError.
+struct Decision { unsigned int choice; double dwell; bool fail; };
+
+// MarkovJumpHMC (markov_jump_hmc.py:366-396): choice 0 = L, 1 = F, 2 = R.
+// ediff_l = H - H_L, ediff_flf = H - H_FLF.
+__device__ __forceinline__ Decision decide_mj(const LaunchParams& p, long long i, unsigned long long attempt,
+                                              double ediff_l, double ediff_flf) {
+    Decision dc; dc.choice = 0; dc.dwell = 0.0; dc.fail = false;
+    const double rl = jump_rate(ediff_l);
+    const double rflf = jump_rate(ediff_flf);
+    if (!(isfinite(rl) && isfinite(rflf))) { dc.fail = true; return dc; }
+    const double rf = rflf - (rl < rflf ? rl : rflf);              // :368
+    const Uniform3 u = draw_uniforms(p, i, attempt, p.p_r != 0.0);
+    const double tl = exp_draw(rl, u.u0);
+    const double tf = exp_draw(rf, u.u1);
+    const double tr = exp_draw(p.p_r, u.u2);
+    dc.dwell = tl;                                                 // min_idx([l, f, r]): first minimum wins
+    if (tf < dc.dwell) { dc.choice = 1; dc.dwell = tf; }
+    if (tr < dc.dwell) { dc.choice = 2; dc.dwell = tr; }
+    return dc;
+}
+
+// ContinuousTimeHMC (markov_jump_hmc.py:261-275): choice 0 = F, 1 = FL, 2 = R.
+__device__ __forceinline__ Decision decide_ct(const LaunchParams& p, long long i, unsigned long long attempt,
+                                              double ediff_fl) {
+    Decision dc; dc.choice = 0; dc.dwell = 0.0; dc.fail = false;
+    const double rfl = jump_rate(ediff_fl);
+    if (!isfinite(rfl)) { dc.fail = true; return dc; }
+    const Uniform3 u = draw_uniforms(p, i, attempt, p.p_r != 0.0);
+    const double tfl = exp_draw(rfl, u.u0);
+    const double tf = exp_draw(1.0, u.u1);
+    const double tr = exp_draw(p.p_r, u.u2);
+    dc.dwell = tf;                                                 // min_idx([f, fl, r]) :271
+    if (tfl < dc.dwell) { dc.choice = 1; dc.dwell = tfl; }
+    if (tr < dc.dwell) { dc.choice = 2; dc.dwell = tr; }
+    return dc;
+}
+
+// HMCBase / HMC / ControlHMC (markov_jump_hmc.py:106-148): bit0 = FL accepted, bit1 = flipped,
+// bit2 = the batch-wide R coin fired.
+__device__ __forceinline__ Decision decide_discrete(const LaunchParams& p, long long i, unsigned long long attempt,
+                                                    double ediff) {
+    Decision dc; dc.dwell = 0.0; dc.fail = false;
+    const double p_acc = ediff < 0.0 ? exp(ediff) : 1.0;           // leap_prob
+    const Uniform3 u = draw_uniforms(p, i, attempt, false);
+    dc.choice = (u.u0 < p_acc ? 1u : 0u) | (u.u1 < p.p_flip ? 2u : 0u) | (draw_coin(p, attempt) < p.p_r ? 4u : 0u);
+    return dc;
+}
+
+__device__ __forceinline__ void report_failure(const LaunchParams& p, int it) {
+    atomicMin(p.counters + (size_t)(blockIdx.x % MJHMC_COUNTER_STRIPES) * MJHMC_N_COUNTERS + MJHMC_CNT_FAIL,
+              (unsigned long long)it);
+}
+
+// ---------------------------------------------------------------- counters
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-reduce NC local counters and add them to this block's counter stripe.
+template <int NC>
+__device__ __forceinline__ void flush_counters(unsigned long long* counters, const unsigned long long (&loc)[NC],
+                                               const int (&slot)[NC]) {
+    __shared__ unsigned long long sm[NC][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const unsigned long long s = warp_sum(loc[c]);
+        if (lane == 0) sm[c][warp] = s;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long* row = counters + (size_t)(blockIdx.x % MJHMC_COUNTER_STRIPES) * MJHMC_N_COUNTERS;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            unsigned long long s = lane < nwarp ? sm[c][lane] : 0ull;
+            s = warp_sum(s);
+            if (lane == 0 && s) atomicAdd(row + slot[c], s);
+        }
+    }
+}
+
+}  // namespace mjhmc

@@ -1,0 +1,245 @@
+// K1+K2+K3: fused leapfrog integrator + transition for register-resident energies.
+//
+// One thread owns one particle.  Its position, momentum and gradient stay in
+// registers across the L leapfrog steps AND across the n_iter sampling iterations
+// of one launch; HBM sees one coalesced read of (X, V) at launch start, one
+// coalesced write per iteration of the recorded sample column (+ dwelling time),
+// and one write of (X, V) at the end.  EX, EV and dEdX of the reference state
+// (samplers/hmc_state.py:28-39) are functions of (X, V) and are recomputed on chip.
+//
+// Replaces, per iteration:
+//   HMCState.leapfrog/L/F/FLF/R            samplers/hmc_state.py:86-129
+//   HMCBase.sampling_iteration             samplers/markov_jump_hmc.py:116-148
+//   ContinuousTimeHMC.sampling_iteration   samplers/markov_jump_hmc.py:251-290
+//   MarkovJumpHMC.sampling_iteration       samplers/markov_jump_hmc.py:355-415
+//   draw_from / min_idx                    misc/utils.py:15-49
+#pragma once
+#include "dists.cuh"
+
+namespace mjhmc {
+
+constexpr int kFusedThreads = 128;
+
+template <typename T, int D>
+__device__ __forceinline__ T kinetic(const T (&v)[D]) {
+    T s = (T)0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) s += v[k] * v[k];
+    return s * (T)0.5;                       // hmc_state.py:49-50
+}
+
+// hmc_state.py:86-100 -- L leapfrog steps; g enters as dEdX(x) and leaves as dEdX(x').
+template <class Dist, typename T, int D>
+__device__ __forceinline__ void leapfrog_L(const Dist& dist, T (&x)[D], T (&v)[D], T (&g)[D],
+                                           T eps, T neg_half_eps, int L) {
+    for (int s = 0; s < L; ++s) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) v[k] += neg_half_eps * g[k];
+#pragma unroll
+        for (int k = 0; k < D; ++k) x[k] += eps * v[k];
+        dist.grad(x, g);
+#pragma unroll
+        for (int k = 0; k < D; ++k) v[k] += neg_half_eps * g[k];
+    }
+}
+
+template <class Dist, typename T, int D>
+__global__ void __launch_bounds__(kFusedThreads)
+fused_sample_kernel(const __grid_constant__ LaunchParams p) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < p.n;
+    const Dist dist(p);
+    const int d = p.d;
+    const T eps = (T)p.eps;
+    const T neg_half_eps = (T)(-p.eps / 2.0);
+    const int L = p.L;
+    const int sampler = p.sampler;
+
+    unsigned long long n_l = 0, n_f = 0, n_fl = 0, n_r = 0, n_E = 0;
+
+    if (live) {
+        T x[D], v[D], g[D];
+        const T* Xin = (const T*)p.Xin;
+        const T* Vin = (const T*)p.Vin;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            x[k] = (k < d) ? Xin[(long long)k * p.ld + i] : (T)0;
+            v[k] = (k < d) ? Vin[(long long)k * p.ld + i] : (T)0;
+        }
+        dist.grad(x, g);
+        T EX = dist.energy(x);
+        T EV = kinetic<T, D>(v);
+
+        bool cached = false;
+        T Hc = (T)0;
+        if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
+            cached = p.ca_in[i] != 0;
+            Hc = ((const T*)p.Hc_in)[i];
+        }
+        double dwell = 0.0;
+
+        for (int it = 0; it < p.n_iter; ++it) {
+            const unsigned long long attempt = p.attempt0 + (unsigned long long)it;
+            const T H = EX + EV;                                   // hmc_state.py:80-84
+            T xt[D], vt[D], gt[D];
+
+            // ---- FLF state (hmc_state.py:109-119): only its energy is ever read
+            T Hflf = Hc;
+            if (sampler == MJHMC_SAMPLER_MARKOV_JUMP && !cached) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) { xt[k] = x[k]; vt[k] = -v[k]; gt[k] = g[k]; }
+                leapfrog_L<Dist, T, D>(dist, xt, vt, gt, eps, neg_half_eps, L);
+                const T EVf = kinetic<T, D>(vt);
+                const T EXf = dist.energy(xt);
+                Hflf = EXf + EVf;
+                n_E += 1;
+            }
+
+            // ---- L state (hmc_state.py:93-100)
+#pragma unroll
+            for (int k = 0; k < D; ++k) { xt[k] = x[k]; vt[k] = v[k]; gt[k] = g[k]; }
+            leapfrog_L<Dist, T, D>(dist, xt, vt, gt, eps, neg_half_eps, L);
+            const T EVl = kinetic<T, D>(vt);
+            const T EXl = dist.energy(xt);
+            const T Hl = EXl + EVl;
+            n_E += 1;
+
+            unsigned int choice;
+            if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
+                const Decision dc = decide_mj(p, i, attempt, (double)(H - Hl), (double)(H - Hflf));
+                if (dc.fail) { report_failure(p, it); break; }
+                choice = dc.choice; dwell = dc.dwell;
+                if (choice == 0) {
+                    Hc = H; cached = true;                          // :399
+#pragma unroll
+                    for (int k = 0; k < D; ++k) { x[k] = xt[k]; v[k] = vt[k]; g[k] = gt[k]; }
+                    EX = EXl; EV = EVl;
+                    n_l += 1;
+                } else if (choice == 1) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) v[k] = -v[k];
+                    cached = false;                                 // :410
+                    n_f += 1;
+                } else {
+                    T z[D];
+                    draw_normals<T, D>(p, i, attempt, d, z);
+#pragma unroll
+                    for (int k = 0; k < D; ++k) v[k] = v[k] * (T)p.r_keep + z[k] * (T)p.r_mix;   // hmc_state.py:126
+                    EV = kinetic<T, D>(v);
+                    cached = false;                                 // :409
+                    n_r += 1;
+                }
+            } else if (sampler == MJHMC_SAMPLER_CONTINUOUS_TIME) {
+                // proposal is F L z (markov_jump_hmc.py:258)
+                const Decision dc = decide_ct(p, i, attempt, (double)(H - Hl));
+                if (dc.fail) { report_failure(p, it); break; }
+                choice = dc.choice; dwell = dc.dwell;
+                if (choice == 1) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) { x[k] = xt[k]; v[k] = -vt[k]; g[k] = gt[k]; }
+                    EX = EXl; EV = EVl;
+                    n_fl += 1;
+                } else if (choice == 0) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) v[k] = -v[k];
+                    n_f += 1;
+                } else {
+                    T z[D];
+                    draw_normals<T, D>(p, i, attempt, d, z);
+#pragma unroll
+                    for (int k = 0; k < D; ++k) v[k] = v[k] * (T)p.r_keep + z[k] * (T)p.r_mix;
+                    EV = kinetic<T, D>(v);
+                    n_r += 1;
+                }
+            } else {
+                const Decision dc = decide_discrete(p, i, attempt, (double)(H - Hl));
+                choice = dc.choice;
+                const bool acc = choice & 1u, flip = choice & 2u;
+                if (acc) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) { x[k] = xt[k]; v[k] = -vt[k]; g[k] = gt[k]; }
+                    EX = EXl; EV = EVl;
+                }
+                if (flip) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) v[k] = -v[k];
+                }
+                if (choice & 4u) {                                  // one coin for the whole batch :138
+                    T z[D];
+                    draw_normals<T, D>(p, i, attempt, d, z);
+#pragma unroll
+                    for (int k = 0; k < D; ++k) v[k] = v[k] * (T)p.r_keep + z[k] * (T)p.r_mix;
+                    EV = kinetic<T, D>(v);
+                    n_r += 1;
+                }
+                n_l += (acc && flip);
+                n_f += (flip && !acc);
+                n_fl += (acc && !flip);
+            }
+
+            // ---- record (markov_jump_hmc.py:169,334)
+            if (p.samples) {
+                T* S = (T*)p.samples + (long long)it * p.s_stride_it + i;
+#pragma unroll
+                for (int k = 0; k < D; ++k)
+                    if (k < d) S[(long long)k * p.s_stride_k] = x[k];
+            }
+            if (p.dwell) p.dwell[(long long)it * p.n + i] = dwell;
+            if (p.choice) p.choice[(long long)it * p.n + i] = (uint8_t)choice;
+        }
+
+        T* Xout = (T*)p.Xout;
+        T* Vout = (T*)p.Vout;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            if (k < d) {
+                Xout[(long long)k * p.ld + i] = x[k];
+                Vout[(long long)k * p.ld + i] = v[k];
+            }
+        }
+        if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
+            p.ca_out[i] = cached ? 1 : 0;
+            ((T*)p.Hc_out)[i] = Hc;
+        }
+        if (p.dwell_last && sampler != MJHMC_SAMPLER_DISCRETE) p.dwell_last[i] = dwell;
+    }
+
+    const unsigned long long loc[6] = {n_l, n_f, n_fl, n_r, n_E, n_E * (unsigned long long)L};
+    const int slot[6] = {MJHMC_CNT_L, MJHMC_CNT_F, MJHMC_CNT_FL, MJHMC_CNT_R, MJHMC_CNT_E, MJHMC_CNT_DEDX};
+    flush_counters<6>(p.counters, loc, slot);
+}
+
+// Host-side launcher for one (Dist, T, D) instantiation.
+template <class Dist, typename T, int D>
+cudaError_t launch_fused(const LaunchParams& p, cudaStream_t stream) {
+    const long long blocks = (p.n + kFusedThreads - 1) / kFusedThreads;
+    if (blocks == 0) return cudaSuccess;
+    fused_sample_kernel<Dist, T, D><<<(unsigned)blocks, kFusedThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// Dispatch table entry point implemented per translation unit (fused_inst_*.cu).
+typedef cudaError_t (*fused_launch_fn)(const LaunchParams&, cudaStream_t);
+fused_launch_fn find_fused_f64(int dist_kind, int D);
+fused_launch_fn find_fused_f32(int dist_kind, int D);
+
+template <typename T, int D>
+fused_launch_fn pick_dist(int kind) {
+    switch (kind) {
+        case MJHMC_DIST_TEST_GAUSSIAN:  return &launch_fused<TestGaussianD<T, D>, T, D>;
+        case MJHMC_DIST_DIAG_GAUSSIAN:  return &launch_fused<DiagGaussianD<T, D>, T, D>;
+        case MJHMC_DIST_ROUGH_WELL:     return &launch_fused<RoughWellD<T, D>, T, D>;
+        case MJHMC_DIST_FUNNEL:         return &launch_fused<FunnelD<T, D, false>, T, D>;
+        case MJHMC_DIST_FUNNEL_LITERAL: return &launch_fused<FunnelD<T, D, true>, T, D>;
+        default: return nullptr;
+    }
+}
+
+// Register-kernel template dimension for a runtime ndims (0 = none).
+inline int fused_template_dim(int d) {
+    static const int dims[] = {1, 2, 3, 4, 6, 8, 10, 16};
+    for (int t : dims) if (d <= t) return t;
+    return 0;
+}
+
+}  // namespace mjhmc

@@ -1,0 +1,55 @@
+"""Host view of the particle state (reference: mjhmc/samplers/hmc_state.py).
+
+On the device only X and V (plus one cached energy and one flag per particle for the FLF
+cache) are stored; EX, EV and dEdX are functions of (X, V).  ``HMCState`` is the numpy view
+callers of the reference read and assign (``sampler.state.X``, ``.V``, ``.EX``, ``.EV``,
+``.dEdX``, ``.H()``, ``.copy()``); the derived arrays are evaluated lazily on the GPU without
+touching the evaluation counters.
+"""
+import numpy as np
+
+
+class HMCState(object):
+    """Holds all the state variables for sampling particles (numpy, float64)."""
+
+    def __init__(self, X, parent, V=None, cache_active=None, H_cache=None):
+        self.parent = parent
+        self.X = np.array(X, dtype=np.float64)
+        self.nbatch = self.X.shape[1]
+        self.V = np.random.randn(*self.X.shape) if V is None else np.array(V, dtype=np.float64)   # hmc_state.py:26
+        self.active_idx = np.arange(self.nbatch)
+        self.cache_active = (np.zeros(self.nbatch, dtype=bool) if cache_active is None
+                             else np.array(cache_active, dtype=bool))
+        self.H_cache = np.zeros(self.nbatch) if H_cache is None else np.array(H_cache, dtype=np.float64)
+
+    # derived arrays (hmc_state.py:28-39, 46-53), evaluated on the device, not counted
+    @property
+    def EX(self):
+        return np.asarray(self.parent._uncounted_E(self.X), dtype=np.float64).reshape((1, -1))
+
+    @property
+    def EV(self):
+        return (np.sum(self.V ** 2, axis=0) / 2.).reshape((1, -1))
+
+    @property
+    def dEdX(self):
+        return np.asarray(self.parent._uncounted_dEdX(self.X), dtype=np.float64)
+
+    def H(self):
+        """returns the full energy of the state (hmc_state.py:80-84)"""
+        return self.EX + self.EV
+
+    def copy(self):
+        return HMCState(self.X.copy(), self.parent, V=self.V.copy(), cache_active=self.cache_active.copy(),
+                        H_cache=self.H_cache.copy())
+
+    def get_state(self):
+        return np.concatenate((self.X, self.V))
+
+    def F(self):
+        """Explicit flip operator (hmc_state.py:102-107)."""
+        self.V = -self.V
+        return self
+
+    def reset_flf_cache(self):
+        self.cache_active = np.zeros_like(self.cache_active)

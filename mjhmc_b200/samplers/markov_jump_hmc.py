@@ -1,0 +1,628 @@
+"""The sampler classes of the reference (mjhmc/samplers/markov_jump_hmc.py) on the GPU.
+
+Same names, constructor arguments, attributes and error behaviour as the reference:
+``HMCBase``, ``HMC``, ``ControlHMC``, ``ContinuousTimeHMC``, ``MarkovJumpHMC`` with
+``sample(n_samples, preserve_order)``, ``sampling_iteration()``, ``burn_in()``, the operator
+counters ``l_count / f_count / fl_count / r_count``, ``dwelling_times``, ``state`` ...
+
+Underneath, one ``sample(n)`` call is one launch of the fused sampler kernel
+(csrc/fused_elementwise.cuh, csrc/dense.cu) that keeps every particle on chip across the n
+iterations; energies that only exist as Python callables run the unfused path
+(kernels for the leapfrog pieces and the transition, the callable in between).
+
+B200-specific keyword arguments (all optional, accepted by every class):
+    dtype            'float64' (default, the reference's arithmetic) or 'float32'
+    seed             Philox key; default: drawn from np.random so np.random.seed() pins a run
+    device           torch device string, default current CUDA device
+    injected_draws   dict(Z=(A,d,N), U=(A,3,N), U0=(A,)) -> INJECT mode (trajectory parity tests)
+    particle_offset  global index of this shard's first particle (multi-GPU sharding)
+    V                initial momentum (default np.random.randn like hmc_state.py:26)
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _device, _lib
+from ..misc.distributions import Distribution
+from ..misc.utils import overrides
+from .hmc_state import HMCState
+
+#pylint: disable=too-many-instance-attributes
+#pylint: disable=too-many-arguments
+
+INFINITE_RATE_MSG = ("Infinite rate. This occurs when calculating transition rates "
+                     "between states that have a very large energy difference, such that "
+                     "the transition probability is less than the numerical precision. "
+                     "Try decreasing the leapfrog stepsize/number of steps or dividing "
+                     " the energy by a large constant.")
+
+_B200_KWARGS = ("dtype", "seed", "device", "injected_draws", "particle_offset", "V")
+
+
+class _CallableEnergy(Distribution):
+    """Wraps the (Xinit, E, dEdX) constructor form (markov_jump_hmc.py:56-65)."""
+
+    def __init__(self, Xinit, E, dEdX):
+        self._E, self._dEdX, self._Xinit = E, dEdX, Xinit
+        super(_CallableEnergy, self).__init__(ndims=Xinit.shape[0], nbatch=Xinit.shape[1])
+
+    def E_val(self, X):
+        return np.asarray(self._E(X)).reshape((1, -1))
+
+    def dEdX_val(self, X):
+        return np.asarray(self._dEdX(X))
+
+    def gen_init_X(self):
+        self.Xinit = self._Xinit
+
+    def __hash__(self):
+        return id(self)
+
+
+def _bound_distribution(E, dEdX):
+    """(dist.E, dist.dEdX) of a built-in distribution -> that distribution (fused path)."""
+    a, b = getattr(E, "__self__", None), getattr(dEdX, "__self__", None)
+    if a is not None and a is b and isinstance(a, Distribution) and \
+            getattr(E, "__name__", "") == "E" and getattr(dEdX, "__name__", "") == "dEdX":
+        return a
+    return None
+
+
+class _Engine(object):
+    """Device state + launches.  Fused when the distribution has a kernel descriptor the
+    library supports, unfused (callback) otherwise."""
+
+    def __init__(self, sampler, distribution, X0, V0, opts):
+        self.sampler = sampler
+        self.dist = distribution
+        self.device = _device.require_cuda(opts.get("device"))
+        self.lib = _lib.load()
+        self.dtype = _device.norm_dtype(opts.get("dtype") or "float64")
+        self.tdtype = _device.torch_dtype(self.dtype)
+        self.code = _device.dtype_code(self.dtype)
+        self.d, self.n = X0.shape
+        self.offset = int(opts.get("particle_offset") or 0)
+        inj = opts.get("injected_draws")
+        self.inj = None
+        if inj is not None:
+            f64 = lambda a: None if a is None else _device.to_device(np.asarray(a, dtype=np.float64), "float64", self.device)
+            self.inj = dict(Z=f64(inj.get("Z")), U=f64(inj.get("U")), U0=f64(inj.get("U0")))
+            self.inj_ld = int(np.asarray(inj["U"]).shape[-1])
+        seed = opts.get("seed")
+        self.seed = int(np.random.randint(0, 2 ** 62)) if seed is None else int(seed)
+        with torch.cuda.device(self.device):
+            desc = distribution.kernel_descriptor(self.dtype, self.device)
+            self.fused = False
+            if desc is not None:
+                self.desc, self._desc_keep = desc
+                self.fused = bool(self.lib.mjhmc_fused_supported(C.byref(self.desc)))
+            mk = lambda a: _device.to_device(a, self.dtype, self.device)
+            self.X = [mk(X0), torch.empty((self.d, self.n), dtype=self.tdtype, device=self.device)]
+            self.V = [mk(V0), torch.empty((self.d, self.n), dtype=self.tdtype, device=self.device)]
+            self.Hc = [torch.zeros(self.n, dtype=self.tdtype, device=self.device) for _ in range(2)]
+            self.ca = [torch.zeros(self.n, dtype=torch.uint8, device=self.device) for _ in range(2)]
+            self.cur = 0
+            tmpl = np.zeros((_lib.COUNTER_STRIPES, _lib.N_COUNTERS), dtype=np.int64)
+            tmpl[:, _lib.CNT_FAIL] = _lib.INT64_MAX
+            self.cnt_template = torch.as_tensor(tmpl, device=self.device)
+            self.counters = self.cnt_template.clone()
+            self.dwell_last = torch.zeros(self.n, dtype=torch.float64, device=self.device)
+            if not self.fused:
+                # the reference's full HMCState (hmc_state.py:28-39): callables cannot be re-evaluated on chip
+                self.G = self._callback(self.X[0], True, count=False)
+                self.EX = self._callback(self.X[0], False, count=False).reshape(-1)
+                self.EV = self._kinetic(self.V[0])
+        self.launches = 0
+
+    # ---------------------------------------------------------------- helpers
+    def _stream(self):
+        return _device.stream_ptr(self.device)
+
+    def _hp(self):
+        s = self.sampler
+        hp = _lib.HP()
+        hp.sampler = s._sampler_code
+        hp.num_leapfrog_steps = int(s.num_leapfrog_steps)
+        hp.epsilon = float(s.epsilon)
+        hp.beta = float(s.beta)
+        hp.p_flip = float(s.p_flip)
+        hp.p_r = float(s.p_r)
+        return hp
+
+    def _rng(self, attempt0):
+        r = _lib.RNG()
+        r.seed = self.seed
+        r.attempt0 = int(attempt0)
+        r.particle0 = self.offset
+        if self.inj is not None:
+            r.mode = _lib.RNG_INJECT
+            r.Z = self.inj["Z"].data_ptr() if self.inj["Z"] is not None else None
+            r.U = self.inj["U"].data_ptr()
+            r.U0 = self.inj["U0"].data_ptr() if self.inj["U0"] is not None else None
+            r.inj_ld = self.inj_ld
+            n_att = self.inj["U"].shape[0]
+            if attempt0 >= n_att:
+                raise IndexError("injected draws exhausted (attempt %d of %d)" % (attempt0, n_att))
+        else:
+            r.mode = _lib.RNG_PHILOX
+        return r
+
+    def _state(self, which):
+        st = _lib.State()
+        st.X = self.X[which].data_ptr()
+        st.V = self.V[which].data_ptr()
+        st.H_cache = self.Hc[which].data_ptr()
+        st.cache_active = self.ca[which].data_ptr()
+        st.n = self.n
+        st.ld = self.n
+        return st
+
+    def _outputs(self, samples, it0, dwell, choice):
+        o = _lib.Outputs()
+        esz = None
+        if samples is not None:
+            esz = samples.element_size()
+            o.samples = samples.data_ptr() + it0 * samples.stride(1) * esz
+            o.stride_k = samples.stride(0)
+            o.stride_it = samples.stride(1)
+        if dwell is not None:
+            o.dwell = dwell.data_ptr() + it0 * self.n * 8
+        if choice is not None:
+            o.choice = choice.data_ptr() + it0 * self.n
+        o.dwell_last = self.dwell_last.data_ptr()
+        o.counters = self.counters.data_ptr()
+        return o
+
+    def _read_counters(self):
+        out = (C.c_int64 * _lib.N_COUNTERS)()
+        _lib.check(self.lib.mjhmc_counters_read(_device.ptr(self.counters), out, self._stream()), "counters_read")
+        return list(out)
+
+    def reset_cache(self):
+        self.ca[self.cur].zero_()
+
+    # ---------------------------------------------------------------- fused launch
+    def launch(self, attempt0, n_iter, samples=None, it0=0, dwell=None, choice=None):
+        """Runs n_iter iterations from the current state into the spare buffers (no commit).
+        Returns the folded counters of this launch."""
+        with torch.cuda.device(self.device):
+            self.counters.copy_(self.cnt_template)
+            if self.fused:
+                hp, rng = self._hp(), self._rng(attempt0)
+                if self.inj is not None and attempt0 + n_iter > self.inj["U"].shape[0]:
+                    raise IndexError("injected draws exhausted")
+                src, dst = self._state(self.cur), self._state(self.cur ^ 1)
+                o = self._outputs(samples, it0, dwell, choice)
+                _lib.check(self.lib.mjhmc_sample_fused(C.byref(self.desc), C.byref(hp), C.byref(rng), C.byref(src),
+                                                       C.byref(dst), int(n_iter), C.byref(o), self._stream()),
+                           "sample_fused")
+                self.launches += 1
+                return self._read_counters()
+            return self._launch_unfused(attempt0, n_iter, samples, it0, dwell, choice)
+
+    def commit(self):
+        if self.fused:
+            self.cur ^= 1
+
+    # ---------------------------------------------------------------- unfused (callback) path
+    def _callback(self, Xd, want_grad, count=True):
+        """Evaluates the distribution's callable on a device array (d, m) -> device array."""
+        dist = self.dist
+        if getattr(dist, "accepts_device_arrays", False):
+            arg = Xd
+        else:
+            arg = Xd.detach().cpu().numpy().astype(np.float64)
+        if want_grad:
+            out = dist.dEdX(arg) if count else dist.dEdX_val(arg)
+        else:
+            out = dist.E(arg) if count else dist.E_val(arg)
+        if isinstance(out, torch.Tensor):
+            return out.to(device=self.device, dtype=self.tdtype).contiguous()
+        return _device.to_device(np.asarray(out, dtype=np.float64), self.dtype, self.device)
+
+    def _kinetic(self, Vd):
+        m = Vd.shape[1]
+        EV = torch.empty(m, dtype=self.tdtype, device=self.device)
+        _lib.check(self.lib.mjhmc_kinetic(self.code, self.d, _device.ptr(Vd), m, m, _device.ptr(EV), self._stream()),
+                   "kinetic")
+        return EV
+
+    def _L(self, X, V, G):
+        """hmc_state.py:93-100 on (d, m) device arrays, in place; returns (G, EX, EV)."""
+        s = self.sampler
+        m = X.shape[1]
+        eps = float(s.epsilon)
+        for _ in range(int(s.num_leapfrog_steps)):
+            _lib.check(self.lib.mjhmc_kick_drift(self.code, self.d, _device.ptr(X), _device.ptr(V), _device.ptr(G),
+                                                 m, m, eps, self._stream()), "kick_drift")
+            G = self._callback(X, True)
+            _lib.check(self.lib.mjhmc_kick(self.code, self.d, _device.ptr(V), _device.ptr(G), m, m, eps,
+                                           self._stream()), "kick")
+        EV = self._kinetic(V)
+        EX = self._callback(X, False).reshape(-1)
+        return G, EX, EV
+
+    def _launch_unfused(self, attempt0, n_iter, samples, it0, dwell, choice):
+        s = self.sampler
+        total = [0] * _lib.N_COUNTERS
+        total[_lib.CNT_FAIL] = _lib.INT64_MAX
+        mj = s._sampler_code == _lib.SAMPLER_MARKOV_JUMP
+        X, V = self.X[0], self.V[0]
+        for it in range(n_iter):
+            H_flf = None
+            if mj:
+                H_flf = torch.zeros(self.n, dtype=self.tdtype, device=self.device)
+                idx = torch.nonzero(self.ca[0] == 0).reshape(-1)
+                if idx.numel():
+                    Xs, Vs, Gs = X[:, idx].contiguous(), (-V[:, idx]).contiguous(), self.G[:, idx].contiguous()
+                    _, EXs, EVs = self._L(Xs, Vs, Gs)
+                    H_flf[idx] = EXs + EVs
+            Xp, Vp = X.clone(), V.clone()
+            Gp, EXp, EVp = self._L(Xp, Vp, self.G.clone())
+            snap = None
+            if s._sampler_code != _lib.SAMPLER_DISCRETE:
+                snap = [t.clone() for t in (X, V, self.G, self.EX, self.EV, self.Hc[0], self.ca[0])]
+            cur = _lib.FullState(X.data_ptr(), V.data_ptr(), self.G.data_ptr(), self.EX.data_ptr(), self.EV.data_ptr())
+            prop = _lib.FullState(Xp.data_ptr(), Vp.data_ptr(), Gp.data_ptr(), EXp.data_ptr(), EVp.data_ptr())
+            hp, rng = self._hp(), self._rng(attempt0 + it)
+            o = self._outputs(samples, it0 + it, dwell, choice)
+            self.counters.copy_(self.cnt_template)
+            _lib.check(self.lib.mjhmc_transition(self.code, self.d, C.byref(hp), C.byref(rng), self.n, self.n,
+                                                 C.byref(cur), C.byref(prop), _device.ptr(H_flf),
+                                                 _device.ptr(self.Hc[0]), _device.ptr(self.ca[0]), C.byref(o),
+                                                 self._stream()), "transition")
+            self.launches += 1
+            cnt = self._read_counters()
+            if cnt[_lib.CNT_FAIL] != _lib.INT64_MAX:
+                for dst, src in zip((X, V, self.G, self.EX, self.EV, self.Hc[0], self.ca[0]), snap):
+                    dst.copy_(src)
+                total[_lib.CNT_FAIL] = it
+                return total
+            for c in (_lib.CNT_L, _lib.CNT_F, _lib.CNT_FL, _lib.CNT_R):
+                total[c] += cnt[c]
+        return total
+
+    # ---------------------------------------------------------------- host views
+    def download(self):
+        c = self.cur
+        return (self.X[c].double().cpu().numpy(), self.V[c].double().cpu().numpy(),
+                self.ca[c].cpu().numpy().astype(bool), self.Hc[c].double().cpu().numpy())
+
+    def upload(self, st):
+        c = self.cur
+        self.X[c].copy_(_device.to_device(st.X, self.dtype, self.device))
+        self.V[c].copy_(_device.to_device(st.V, self.dtype, self.device))
+        self.ca[c].copy_(torch.as_tensor(np.asarray(st.cache_active, dtype=np.uint8), device=self.device))
+        self.Hc[c].copy_(_device.to_device(st.H_cache, self.dtype, self.device))
+        if not self.fused:
+            self.G = self._callback(self.X[0], True, count=False)
+            self.EX = self._callback(self.X[0], False, count=False).reshape(-1)
+            self.EV = self._kinetic(self.V[0])
+
+
+class HMCBase(object):
+    """
+    The base class for all HMC samplers in this file.
+    Not a useful sampler in of itself but provides a useful structure
+      and serves as a control
+    """
+    _sampler_code = _lib.SAMPLER_DISCRETE
+
+    def __init__(self, Xinit=None, E=None, dEdX=None,
+                 epsilon=1e-4, alpha=0.2, beta=None,
+                 num_leapfrog_steps=5, distribution=None, **b200):
+        unknown = set(b200) - set(_B200_KWARGS)
+        if unknown:
+            raise TypeError("__init__() got an unexpected keyword argument %r" % sorted(unknown)[0])
+        self._opts = b200
+        self._engine = None
+        self._host_state = None
+        self._attempt = 0
+        # do not execute this block if I am an instance of MarkovJumpHMC (markov_jump_hmc.py:46)
+        if not isinstance(self, MarkovJumpHMC):
+            if isinstance(distribution, Distribution):
+                distribution.mjhmc = False
+                distribution.reset()
+                self._bind(distribution)
+            else:
+                assert Xinit is not None
+                assert E is not None
+                assert dEdX is not None
+                bound = _bound_distribution(E, dEdX)
+                if bound is not None and bound.kernel_descriptor("float64", None if not torch.cuda.is_available() else "cuda") is not None:
+                    bound.Xinit = np.array(Xinit)
+                    bound.nbatch = Xinit.shape[1]
+                    self._bind(bound)
+                else:
+                    self._bind(_CallableEnergy(np.array(Xinit), E, dEdX))
+
+        self.num_leapfrog_steps = num_leapfrog_steps
+        self.epsilon = epsilon
+        self.beta = beta or alpha**(1./(self.epsilon*self.num_leapfrog_steps))
+
+        self.original_epsilon = epsilon
+        self.original_l = self.num_leapfrog_steps
+
+        self.n_burn_in = 500
+
+        # these settings for the base class only
+        self.p_flip = 0.5
+        self.p_r = 1
+
+        # total operator counts. counted per particle
+        self.l_count = 0
+        self.f_count = 0
+        # this one is necessary since we're not always flipping the momentum
+        self.fl_count = 0
+        self.r_count = 0
+
+        # only approximate!! lower bound
+        self.grad_per_sample_step = self.num_leapfrog_steps
+
+    # ------------------------------------------------------------------ construction
+    def _bind(self, distribution):
+        """Builds the device state: HMCState(Xinit.copy(), self) of markov_jump_hmc.py:54,233."""
+        self.distribution = distribution
+        self.ndims = distribution.Xinit.shape[0]
+        self.nbatch = distribution.Xinit.shape[1]
+        self.energy_func = distribution.E
+        self.grad_func = distribution.dEdX
+        X0 = distribution.Xinit
+        V0 = self._opts.get("V")
+        if V0 is None:
+            V0 = np.random.randn(self.ndims, self.nbatch)       # hmc_state.py:26
+        self._engine = _Engine(self, distribution, X0, V0, self._opts)
+        if self._engine.fused:
+            # the state constructor evaluates E and dEdX once (hmc_state.py:28-39); here both are
+            # recomputed on chip whenever needed, so only the counters move
+            distribution.E_count += self.nbatch
+            distribution.dEdX_count += self.nbatch
+        else:
+            # the callbacks did run (uncounted above); count them like the reference
+            distribution.E_count += self.nbatch
+            distribution.dEdX_count += self.nbatch
+        self._host_state = None
+
+    # to deprecate
+    def E(self, X):
+        """compute energy function at X"""
+        return np.asarray(self.energy_func(X)).reshape((1, -1))
+
+    # to deprecate
+    def dEdX(self, X):
+        """compute energy function gradient at X"""
+        return self.grad_func(X)
+
+    def _uncounted_E(self, X):
+        return self.distribution.E_val(X)
+
+    def _uncounted_dEdX(self, X):
+        return self.distribution.dEdX_val(X)
+
+    # ------------------------------------------------------------------ state view
+    @property
+    def state(self):
+        if self._host_state is None:
+            X, V, ca, Hc = self._engine.download()
+            self._host_state = HMCState(X, self, V=V, cache_active=ca, H_cache=Hc)
+        return self._host_state
+
+    @state.setter
+    def state(self, st):
+        self._host_state = st
+
+    def _sync_state_to_device(self):
+        """A handed-out HMCState may have been edited (or replaced) by the caller."""
+        if self._host_state is not None:
+            self._engine.upload(self._host_state)
+            self._host_state = None
+
+    @property
+    def dwelling_times(self):
+        return self._engine.dwell_last.cpu().numpy()
+
+    # ------------------------------------------------------------------ iteration driver
+    def _accumulate(self, cnt, transitions=True):
+        if transitions:
+            self.l_count += cnt[_lib.CNT_L]
+            self.f_count += cnt[_lib.CNT_F]
+            self.fl_count += cnt[_lib.CNT_FL]
+            self.r_count += cnt[_lib.CNT_R]
+        if self._engine.fused:
+            self.distribution.E_count += cnt[_lib.CNT_E]
+            self.distribution.dEdX_count += cnt[_lib.CNT_DEDX]
+
+    def _run(self, n, samples=None, it0=0, dwell=None, choice=None):
+        """n sampling iterations, incl. the infinite-rate protocol (markov_jump_hmc.py:364-389)."""
+        eng = self._engine
+        done = 0
+        while done < n:
+            m = n - done
+            cnt = eng.launch(self._attempt, m, samples, it0 + done, dwell, choice)
+            fail = cnt[_lib.CNT_FAIL]
+            if fail == _lib.INT64_MAX:
+                eng.commit()
+                self._accumulate(cnt)
+                self._attempt += m
+                done += m
+                continue
+            if eng.fused:
+                if fail > 0:
+                    # replay the iterations before the failing one (deterministic streams), keep them
+                    cnt = eng.launch(self._attempt, fail, samples, it0 + done, dwell, choice)
+                    assert cnt[_lib.CNT_FAIL] == _lib.INT64_MAX
+                    eng.commit()
+                    self._accumulate(cnt)
+                # the failed attempt: its energy / gradient evaluations stay counted, nothing else happens
+                cnt = eng.launch(self._attempt + fail, 1)
+                self._accumulate(cnt, transitions=False)
+            else:
+                # the unfused engine advanced in place up to the failing iteration and restored it
+                self._accumulate(cnt)
+            self._attempt += fail
+            done += fail
+            self._attempt += 1
+            self._on_infinite_rate(samples, it0 + done, dwell, choice)
+            done += 1
+
+    def _on_infinite_rate(self, samples, it, dwell, choice):
+        raise ValueError(INFINITE_RATE_MSG)
+
+    def _advance(self, n, record=True, want_dwell=False, want_choice=False):
+        eng = self._engine
+        self._sync_state_to_device()
+        samples = dwell = choice = None
+        with torch.cuda.device(eng.device):
+            if record:
+                samples = torch.empty((self.ndims, n, self.nbatch), dtype=eng.tdtype, device=eng.device)
+            if want_dwell:
+                dwell = torch.empty((n, self.nbatch), dtype=torch.float64, device=eng.device)
+            if want_choice:
+                choice = torch.empty((n, self.nbatch), dtype=torch.uint8, device=eng.device)
+            self._run(n, samples, 0, dwell, choice)
+        return samples, dwell, choice
+
+    def sampling_iteration(self):
+        """Perform a single sampling step"""
+        self._advance(1, record=False)
+
+    def sample_device(self, n_samples=1000):
+        """B200 extension: like sample() but returns the device tensor (ndims, n_samples, nbatch)
+        without the device->host copy."""
+        return self._advance(n_samples)[0]
+
+    def sample(self, n_samples=1000, preserve_order=False, num_steps=None):
+        """
+        Draws nsamples, returns them all
+
+        Args:
+           n_samples: number of samples to draw - int  (``num_steps`` is accepted as an alias, README.md:35)
+           preserve_order: if True, time is given it's own axis.
+              otherwise, it is rolled into the batch axis
+
+        Returns:
+           if preserve_order:
+               samples - [n_dim, n_batch, n_samples]
+           else:
+               samples - [n_dim, n_batch * n_samples]
+        """
+        if num_steps is not None:
+            n_samples = num_steps
+        S = self._advance(n_samples)[0]
+        return self._to_host(S, preserve_order)
+
+    def _to_host(self, S, preserve_order):
+        d, n, N = S.shape
+        if preserve_order:
+            return S.permute(0, 2, 1).contiguous().cpu().numpy().astype(np.float64, copy=False)
+        return S.reshape(d, n * N).cpu().numpy().astype(np.float64, copy=False)
+
+    def burn_in(self):
+        """Runs the sample for a number of burn in sampling iterations"""
+        self._advance(self.n_burn_in, record=False)
+
+
+class HMC(HMCBase):
+    """Implements standard HMC
+    """
+
+    def __init__(self, *args, **kwargs):
+        super(HMC, self).__init__(*args, **kwargs)
+        self.p_flip = 1
+
+
+class ControlHMC(HMCBase):
+    """Standard HMC but randomize all of the momentum some of the time
+    """
+
+    def __init__(self, *args, **kwargs):
+        super(ControlHMC, self).__init__(*args, **kwargs)
+        self.p_flip = 1
+        with np.errstate(divide='ignore'):
+            self.p_r = - np.log(1 - self.beta) * 0.5
+        # tells hmc state to randomize all of the momentum when R is called
+        self.beta = 1
+
+
+class ContinuousTimeHMC(HMCBase):
+    """Base class for all markov jump HMC samplers
+    """
+    _sampler_code = _lib.SAMPLER_CONTINUOUS_TIME
+
+    def __init__(self, *args, **kwargs):
+        """ Initalizer method for continuous-time samplers
+
+        :param resample: boolean flag whether to resample or not. ALWAYS set to true unless you
+           have a specific reason not to. Produced samples will be biased if resample is false
+        """
+        self.resample = kwargs.pop('resample', True)
+        distribution = kwargs.get('distribution')
+        super(ContinuousTimeHMC, self).__init__(*args, **kwargs)
+        # transformation from discrete beta to insure matching autocorrelation
+        with np.errstate(divide='ignore'):
+            self.p_r = - np.log(1 - self.beta) * 0.5
+        # tells hmc state to randomize all of the momentum when R is called
+        self.beta = 1
+
+        if isinstance(distribution, Distribution):
+            distribution.mjhmc = True
+            if not distribution.generation_instance:
+                distribution.reset()
+            self._bind(distribution)
+        else:
+            raise NotImplementedError(
+                ("Unfortunately, you must define your distribution by"
+                 " subclassing mjhmc.misc.Distribution."
+                 "This is due to subtle issues having to do with generating"
+                 " a fair initialization for"
+                 "the embedded Markov Chain. See the docs in mjhmc.misc.Distribution."
+                ))
+
+    @overrides(HMCBase)
+    def sample(self, n_samples=1000, preserve_order=False, num_steps=None):
+        """ Runs sampler and returns a list of n_samples (resampled to be fair)
+
+        preserve_order has no effect if resample is enabled (markov_jump_hmc.py:293-338).
+        """
+        if num_steps is not None:
+            n_samples = num_steps
+        if not self.resample:
+            return self._to_host(self._advance(n_samples)[0], preserve_order)
+        eng = self._engine
+        # 1 + n iterations; sample k is paired with the dwelling time recorded before iteration k+1
+        S, dwell, _ = self._advance(n_samples + 1, want_dwell=True)
+        n, N, d = n_samples, self.nbatch, self.ndims
+        m = n * N
+        dwell_t = dwell[:n].reshape(-1)
+        total_t = np.sum(dwell_t.cpu().numpy())
+        r = np.sort(np.random.random(m)) * total_t
+        with torch.cuda.device(eng.device):
+            r_d = torch.as_tensor(r, device=eng.device)
+            out = torch.zeros((d, m), dtype=eng.tdtype, device=eng.device)
+            nbytes = int(eng.lib.mjhmc_resample_scratch_bytes(m))
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=eng.device)
+            _lib.check(eng.lib.mjhmc_resample(eng.code, d, _device.ptr(dwell_t), m, _device.ptr(r_d), m,
+                                              _device.ptr(S), S.stride(0), _device.ptr(out), m, None,
+                                              _device.ptr(scratch), eng._stream()), "resample")
+            return out.cpu().numpy().astype(np.float64, copy=False)
+
+
+class MarkovJumpHMC(ContinuousTimeHMC):
+    """This class implements Markov Jump HMC as described in http://arxiv.org/abs/1509.03808
+    """
+    _sampler_code = _lib.SAMPLER_MARKOV_JUMP
+
+    @overrides(ContinuousTimeHMC)
+    def _on_infinite_rate(self, samples, it, dwell, choice):
+        # infinite rate due to taking too large of a step (markov_jump_hmc.py:376-389):
+        # take smaller steps, but go the same overall distance -- for the whole batch
+        self.epsilon *= 0.5
+        self.num_leapfrog_steps *= 2
+        depth = np.log(self.original_epsilon / self.epsilon) / np.log(2)
+        print("Ecountered infinite rate, doubling back. Depth: {}".format(depth))
+        self._engine.reset_cache()
+        self._run(1, samples, it, dwell, choice)
+        # restore the old guys
+        self.epsilon *= 2
+        self.num_leapfrog_steps = int(self.num_leapfrog_steps / 2)

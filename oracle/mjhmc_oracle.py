@@ -562,3 +562,28 @@ def ess_from_autocor(ac):
             break
         s += ac[tau]
     return T / (1.0 + 2.0 * s)
+
+
+class FastNumpyDraws(object):
+    """Vectorised draws from a numpy Generator: same distributions as the reference's
+    per-particle ``np.random.exponential`` loop (utils.py:31-49) without the Python loop.
+    Used only as the CPU-baseline configuration of bench.py (a faster, hence more
+    conservative, baseline than the reference's own loop)."""
+
+    def __init__(self, seed=0):
+        self.g = np.random.default_rng(seed)
+
+    def normals(self, attempt, ndims, n):
+        return self.g.standard_normal((ndims, n))
+
+    def uniforms(self, attempt, slot, n):
+        return self.g.random(n)
+
+    def coin(self, attempt):
+        return float(self.g.random())
+
+    def exponentials(self, attempt, slot, rates):
+        return _exp_from_uniform(rates, self.g.random(len(rates)))
+
+    def resample_uniforms(self, m):
+        return self.g.random(m)

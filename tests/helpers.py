@@ -42,3 +42,49 @@ def oracle_from_golden(name, g, draws=None):
     return orc.OracleSampler(kind, energy_from_golden(g), g["X0"], V=g["V0"], epsilon=float(g["epsilon"]),
                              beta=float(g["beta_arg"]), num_leapfrog_steps=int(g["L"]), draws=draws,
                              resample=False)
+
+
+# ----------------------------------------------------------------------------
+# product side (GPU)
+# ----------------------------------------------------------------------------
+def pin_init(dist, X0):
+    """Make a product Distribution always (re)initialise to X0."""
+    X0 = np.array(X0, dtype=np.float64)
+
+    def gen():
+        dist.Xinit = X0.copy()
+    dist.gen_init_X = gen
+    dist.Xinit = X0.copy()
+    dist.nbatch = X0.shape[1]
+    return dist
+
+
+def product_distribution(dist_name, params, d, N):
+    from mjhmc_b200.misc import distributions as D
+    if dist_name == "RoughWell":
+        return D.RoughWell(ndims=d, nbatch=N, scale1=params[0], scale2=params[1])
+    if dist_name == "TestGaussian":
+        return D.TestGaussian(ndims=d, nbatch=N, sigma=params[0])
+    if dist_name == "Gaussian":
+        return D.Gaussian(ndims=d, nbatch=N, J=np.asarray(params))
+    raise KeyError(dist_name)
+
+
+def product_from_golden(name, g, dtype="float64", draws=None, **kw):
+    from mjhmc_b200.samplers import markov_jump_hmc as S
+    kind = name.split("_")[0]
+    d, N = g["X0"].shape
+    dist = pin_init(product_distribution(str(g["dist"]), g["dist_params"], d, N), g["X0"])
+    if draws is None:
+        draws = dict(Z=g["Z"], U=g["U"], U0=g["U0"])
+    extra = dict(resample=False) if kind in ("ContinuousTimeHMC", "MarkovJumpHMC") else {}
+    extra.update(kw)
+    return getattr(S, kind)(distribution=dist, epsilon=float(g["epsilon"]), beta=float(g["beta_arg"]),
+                            num_leapfrog_steps=int(g["L"]), V=g["V0"], dtype=dtype, injected_draws=draws,
+                            **extra), dist
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = max(np.max(np.abs(b)), 1e-300)
+    return float(np.max(np.abs(a - b)) / scale)

@@ -1,0 +1,193 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden reference trajectories
+and against the oracle on the same injected draws.
+
+Tolerances (north_star): trajectories 1e-10 relative in fp64, 1e-4 relative in fp32 (relative
+to the largest magnitude of the compared array); integer counters and operator choices exact.
+"""
+import numpy as np
+import pytest
+
+from oracle import mjhmc_oracle as orc
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"float64": 1e-10, "float32": 1e-4}
+CASES = [c for c in helpers.golden_inject_cases() if not c.endswith("backoff")]
+
+
+def _counters(sampler, dist):
+    return [sampler.l_count, sampler.f_count, sampler.fl_count, sampler.r_count, dist.E_count, dist.dEdX_count]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_trajectory_per_iteration_fp64(name):
+    """One launch per sampling_iteration(); state, energies, dwell times and counters after each."""
+    g = helpers.load_inject(name)
+    s, dist = helpers.product_from_golden(name, g)
+    assert s._engine.fused
+    for it in range(g["X"].shape[0]):
+        s.sampling_iteration()
+        st = s.state
+        assert helpers.rel_err(st.X, g["X"][it]) < TOL["float64"], (name, it)
+        assert helpers.rel_err(st.V, g["V"][it]) < TOL["float64"], (name, it)
+        assert helpers.rel_err(st.EX[0], g["EX"][it]) < TOL["float64"]
+        assert helpers.rel_err(st.EV[0], g["EV"][it]) < TOL["float64"]
+        assert _counters(s, dist) == list(g["counters"][it]), (name, it)
+        if name.startswith(("MarkovJumpHMC", "ContinuousTimeHMC")):
+            fin = np.isfinite(g["dwell"][it])
+            assert np.array_equal(np.isfinite(s.dwelling_times), fin)
+            assert helpers.rel_err(s.dwelling_times[fin], g["dwell"][it][fin]) < 1e-9
+        if name.startswith("MarkovJumpHMC"):
+            assert np.array_equal(st.cache_active, g["cache"][it])
+        s._host_state = None      # do not round-trip the state through the host
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_trajectory_single_launch_fp64(name):
+    """sample(n): all iterations inside ONE persistent launch; every recorded sample column."""
+    g = helpers.load_inject(name)
+    s, dist = helpers.product_from_golden(name, g)
+    n = g["X"].shape[0]
+    X = s.sample(n)
+    d, N = g["X0"].shape
+    assert X.shape == (d, n * N) and X.dtype == np.float64
+    expect = np.concatenate(list(g["X"]), axis=1)
+    assert helpers.rel_err(X, expect) < TOL["float64"]
+    assert helpers.rel_err(s.state.V, g["V"][-1]) < TOL["float64"]
+    assert _counters(s, dist) == list(g["counters"][-1])
+    assert s._engine.launches == 1
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_single_iteration_from_oracle_state_fp32(name):
+    """fp32: each iteration restarted from the oracle's fp64 state (no error accumulation)."""
+    g = helpers.load_inject(name)
+    o = helpers.oracle_from_golden(name, g)
+    s, dist = helpers.product_from_golden(name, g, dtype="float32")
+    mismatched = 0
+    for it in range(g["X"].shape[0]):
+        st = s.state
+        st.X[:], st.V[:] = o.X, o.V
+        st.cache_active[:], st.H_cache[:] = o.cache_active, o.H_cache
+        s._attempt = o.attempt
+        o.sampling_iteration()
+        s.sampling_iteration()
+        got = s.state
+        # a float32 near-tie may pick another operator for a particle: count, do not compare those
+        same = np.all(np.abs(got.X - o.X) <= 1e-3 * (1 + np.abs(o.X)), axis=0) & \
+            np.all(np.abs(got.V - o.V) <= 1e-3 * (1 + np.abs(o.V)), axis=0)
+        mismatched += int((~same).sum())
+        assert helpers.rel_err(got.X[:, same], o.X[:, same]) < TOL["float32"], (name, it)
+        assert helpers.rel_err(got.V[:, same], o.V[:, same]) < TOL["float32"], (name, it)
+    assert mismatched <= 2, "too many operator-choice flips in float32: %d" % mismatched
+
+
+def test_backoff_golden():
+    """Infinite-rate back-off (markov_jump_hmc.py:376-389) against the reference trajectory."""
+    name = "MarkovJumpHMC_backoff"
+    g = helpers.load_inject(name)
+    s, dist = helpers.product_from_golden(name, g)
+    for it in range(g["X"].shape[0]):
+        s.sampling_iteration()
+        st = s.state
+        assert helpers.rel_err(st.X, g["X"][it]) < 1e-10
+        assert helpers.rel_err(st.V, g["V"][it]) < 1e-10
+        assert _counters(s, dist) == list(g["counters"][it])
+        assert s._attempt == int(g["attempts"][it])
+        assert np.array_equal(st.cache_active, g["cache"][it])
+        s._host_state = None
+    assert s.epsilon == float(g["final_epsilon"]) and s.num_leapfrog_steps == int(g["final_L"])
+
+
+def test_backoff_inside_multi_iteration_launch():
+    """The same back-off when the failing iteration sits in the middle of one sample(n) launch."""
+    name = "MarkovJumpHMC_backoff"
+    g = helpers.load_inject(name)
+    s, dist = helpers.product_from_golden(name, g)
+    n = g["X"].shape[0]
+    X = s.sample(n)
+    assert helpers.rel_err(X, np.concatenate(list(g["X"]), axis=1)) < 1e-10
+    assert _counters(s, dist) == list(g["counters"][-1])
+    assert s._attempt == int(g["attempts"][-1])
+
+
+def test_continuous_time_raises_on_infinite_rate():
+    from mjhmc_b200.samplers.markov_jump_hmc import ContinuousTimeHMC
+    from mjhmc_b200.misc.distributions import TestGaussian
+    dist = helpers.pin_init(TestGaussian(ndims=1, nbatch=4), np.array([[100., .1, .2, .3]]))
+    c = ContinuousTimeHMC(distribution=dist, epsilon=1.0, beta=0.5, num_leapfrog_steps=1, V=np.zeros((1, 4)), seed=1)
+    e0 = dist.E_count
+    with pytest.raises(ValueError, match="Infinite rate"):
+        c.sampling_iteration()
+    assert dist.E_count - e0 == 4                      # the failed attempt's evaluations stay counted
+    np.testing.assert_array_equal(c.state.X, [[100., .1, .2, .3]])
+
+
+@pytest.mark.parametrize("kind", orc.KINDS)
+@pytest.mark.parametrize("dist_name", ["RoughWell", "Funnel", "FunnelLiteral", "Gaussian10"])
+def test_philox_mode_matches_oracle_with_numpy_philox(kind, dist_name):
+    """PHILOX mode on the GPU == oracle fed by the numpy restatement of the same stream."""
+    rs = np.random.RandomState(42)
+    from mjhmc_b200.misc import distributions as D
+    from mjhmc_b200.samplers import markov_jump_hmc as S
+    N = 257
+    if dist_name == "RoughWell":
+        d, dist, energy = 2, D.RoughWell(2, N, scale1=5, scale2=4), orc.RoughWellEnergy(5, 4)
+        X0 = rs.randn(d, N) * 3
+    elif dist_name.startswith("Funnel"):
+        lit = dist_name.endswith("Literal")
+        d, dist, energy = 4, D.Funnel(scale=2.0, nbatch=N, ndims=4, literal_reference_energy=lit), orc.FunnelEnergy(2.0, lit)
+        X0 = rs.randn(d, N) * 0.5
+    else:
+        d = 10
+        dist, energy = D.Gaussian(ndims=d, nbatch=N, log_conditioning=1), orc.GaussianEnergy.log_conditioned(d, 1)
+        X0 = rs.randn(d, N)
+    V0 = rs.randn(d, N)
+    helpers.pin_init(dist, X0)
+    hp = dict(epsilon=0.2, beta=0.3, num_leapfrog_steps=3)
+    n = 6
+    if dist_name == "FunnelLiteral":
+        # the graph as written is unbounded below: keep the horizon short enough to stay finite
+        hp, n = dict(epsilon=0.02, beta=0.3, num_leapfrog_steps=2), 3
+    extra = dict(resample=False) if kind in ("ContinuousTimeHMC", "MarkovJumpHMC") else {}
+    seed, offset = 987654321, 1000
+    s = getattr(S, kind)(distribution=dist, V=V0, seed=seed, particle_offset=offset, **hp, **extra)
+    o = orc.OracleSampler(kind, energy, X0, V=V0, draws=orc.PhiloxDraws(seed, offset), resample=False, **hp)
+    X = s.sample(n)
+    Xo = o.sample(n)
+    assert np.all(np.isfinite(Xo))
+    assert helpers.rel_err(X, Xo) < 1e-9
+    assert helpers.rel_err(s.state.V, o.V) < 1e-9
+    c = o.counters()
+    assert _counters(s, dist) == [c["l"], c["f"], c["fl"], c["r"], c["E"], c["dEdX"]]
+
+
+def test_energy_gradient_kernels_match_oracle():
+    from mjhmc_b200.misc import distributions as D
+    rs = np.random.RandomState(3)
+    W = rs.randn(7, 7) * 0.4
+    nu = rs.rand(7) * 2 + 2.1
+    J = rs.randn(6, 6)
+    cases = [
+        (D.RoughWell(3, 50, 7.0, 3.0), orc.RoughWellEnergy(7.0, 3.0), 3),
+        (D.TestGaussian(4, 50, 1.7), orc.TestGaussianEnergy(1.7), 4),
+        (D.Gaussian(5, 50, log_conditioning=3), orc.GaussianEnergy.log_conditioned(5, 3), 5),
+        (D.Gaussian(6, 50, J=J), orc.GaussianEnergy(J), 6),
+        (D.Gaussian(40, 50, log_conditioning=2), orc.GaussianEnergy.log_conditioned(40, 2), 40),
+        (D.Funnel(scale=3.0, nbatch=50, ndims=6), orc.FunnelEnergy(3.0), 6),
+        (D.Funnel(scale=1.5, nbatch=50, ndims=6, literal_reference_energy=True), orc.FunnelEnergy(1.5, True), 6),
+        (D.ProductOfT(ndims=7, nbasis=7, nbatch=50, W=W, lognu=np.log(nu), b=rs.randn(7) * 0.1),
+         orc.ProductOfTEnergy(W, nu.astype('float32'), (rs.randn(0) if False else None)), 7),
+    ]
+    for dist, energy, d in cases:
+        X = rs.randn(d, 33)
+        if isinstance(energy, orc.ProductOfTEnergy):
+            energy = orc.ProductOfTEnergy(dist.weights, dist.nu, dist.bias)
+        e0, g0 = dist.E_count, dist.dEdX_count
+        E = dist.E(X)
+        G = dist.dEdX(X)
+        assert E.shape == (1, 33) and G.shape == (d, 33)
+        assert (dist.E_count - e0, dist.dEdX_count - g0) == (33, 33)
+        assert helpers.rel_err(E[0], energy.E(X)) < 1e-12, type(dist).__name__
+        assert helpers.rel_err(G, energy.dEdX(X)) < 1e-12, type(dist).__name__
