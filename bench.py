@@ -35,13 +35,13 @@ import numpy as np
 WORKLOADS = {
     # configs[1] of BASELINE.json: the configuration the metric is quoted on
     "roughwell2d_mjhmc": dict(dist="RoughWell", ndims=2, n=1_000_000, sampler="MarkovJumpHMC",
-                              epsilon=3.0, beta=0.012314380146563053, L=25, iters=8,
+                              epsilon=3.0, beta=0.012314380146563053, L=25, iters=64,
                               source="search/MJHMC_rw/params.json"),
     "roughwell2d_control": dict(dist="RoughWell", ndims=2, n=1_000_000, sampler="ControlHMC",
-                                epsilon=0.6687788963317871, beta=0.5385961532592773, L=22, iters=8,
+                                epsilon=0.6687788963317871, beta=0.5385961532592773, L=22, iters=64,
                                 source="search/control_rw/params_new.json"),
     "funnel10d_cthmc": dict(dist="Funnel", ndims=10, n=4_000_000, sampler="ContinuousTimeHMC",
-                            epsilon=0.1, beta=0.5, L=10, iters=4, source="search/MJHMC_funnel/config.json midpoints"),
+                            epsilon=0.1, beta=0.5, L=10, iters=16, source="search/MJHMC_funnel/config.json midpoints"),
     # HBM-bound points of the fused leapfrog (one iteration per launch, L = 1)
     "testgauss2d_control_L1": dict(dist="TestGaussian", ndims=2, n=16_000_000, sampler="ControlHMC",
                                    epsilon=0.5, beta=0.1, L=1, iters=1, source="HBM roofline point"),
@@ -245,7 +245,7 @@ def run_b200(args, w):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    g0, launches0 = dist.dEdX_count, eng.launches
+    g0, x0, launches0 = dist.dEdX_count, sampler.grad_evals_executed, eng.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
@@ -259,15 +259,16 @@ def run_b200(args, w):
     t_wall = time.perf_counter() - t_wall0
     clk = clocks.stop() if rank == 0 else None
     ms = sum(a.elapsed_time(b) for a, b in ev)
-    grads = dist.dEdX_count - g0
+    grads = sampler.grad_evals_executed - x0          # leapfrog steps actually integrated on the device
+    grads_ref = dist.dEdX_count - g0                  # the reference's dEdX_count accounting
     launches = eng.launches - launches0
     tt = torch.tensor([ms], dtype=torch.float64, device=dev)
-    gg = torch.tensor([grads, launches], dtype=torch.int64, device=dev)
+    gg = torch.tensor([grads, launches, grads_ref], dtype=torch.int64, device=dev)
     if world > 1:
         dist_pkg.all_reduce(tt, op=dist_pkg.ReduceOp.MAX)
         dist_pkg.all_reduce(gg, op=dist_pkg.ReduceOp.SUM)          # counters: the only cross-GPU reduction
     ms_max = float(tt.item())
-    grads_all, launches_all = int(gg[0].item()), int(gg[1].item())
+    grads_all, launches_all, grads_ref_all = int(gg[0].item()), int(gg[1].item()), int(gg[2].item())
     value = grads_all / (ms_max * 1e-3)
 
     # ---- e2e: host buffers in, host samples out, through the public API, every step
@@ -276,7 +277,7 @@ def run_b200(args, w):
     Vh = torch.as_tensor(V0).pin_memory().numpy()
     e2e_steps = max(1, min(args.steps, 5))
     barrier()
-    g1 = dist.dEdX_count
+    g1 = sampler.grad_evals_executed
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         st = HMCState.__new__(HMCState)
@@ -288,7 +289,7 @@ def run_b200(args, w):
     barrier()
     e2e_t = time.perf_counter() - t0
     ee = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
-    ge = torch.tensor([dist.dEdX_count - g1], dtype=torch.int64, device=dev)
+    ge = torch.tensor([sampler.grad_evals_executed - g1], dtype=torch.int64, device=dev)
     if world > 1:
         dist_pkg.all_reduce(ee, op=dist_pkg.ReduceOp.MAX)
         dist_pkg.all_reduce(ge, op=dist_pkg.ReduceOp.SUM)
@@ -324,7 +325,10 @@ def run_b200(args, w):
             "gpu_launches": launches_all,
             "clocks": clk,
             "wall_s_timed_region": t_wall,
-            "grad_evals": grads_all,
+            "grad_evals_executed": grads_all,
+            "dEdX_count_delta": grads_ref_all,
+            "dEdX_count_rate": grads_ref_all / (ms_max * 1e-3),
+            "particle_iterations_per_s": w["n"] * world * iters * args.steps / (ms_max * 1e-3),
         }
         print(json.dumps(line))
     if world > 1:

@@ -58,7 +58,8 @@ enum {
     MJHMC_CNT_L = 0, MJHMC_CNT_F = 1, MJHMC_CNT_FL = 2, MJHMC_CNT_R = 3, /* markov_jump_hmc.py:82-87 */
     MJHMC_CNT_E = 4, MJHMC_CNT_DEDX = 5,                                 /* distributions.py:44-48,62-75 */
     MJHMC_CNT_FAIL = 6,  /* first iteration (relative to the launch) with a non-finite rate, else INT64_MAX */
-    MJHMC_CNT_SPARE = 7,
+    MJHMC_CNT_EXEC = 7,  /* gradient evaluations actually executed on the device: < DEDX when the energy of
+                            an FLF state is taken from the cache instead of being re-integrated */
     MJHMC_N_COUNTERS = 8
 };
 /* the kernels stripe their atomics over this many counter rows; mjhmc_counters_reduce folds them */
@@ -105,7 +106,8 @@ typedef struct mjhmc_rng {
 typedef struct mjhmc_state {
     void    *X, *V;             /* (ndims, n), row stride ld */
     void    *H_cache;           /* (n,) dtype; MarkovJumpHMC only, else NULL */
-    uint8_t *cache_active;      /* (n,)        MarkovJumpHMC only, else NULL */
+    uint8_t *cache_active;      /* (n,) flags  MarkovJumpHMC only, else NULL: bit0 = the reference's cache_active,
+                                   bit1 = H_cache holds a valid FLF energy (also set after an F move) */
     int64_t  n;                 /* particles in this shard */
     int64_t  ld;
 } mjhmc_state;

@@ -8,14 +8,14 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmjhmc_b200.so")
+LIB_PATH = os.environ.get("MJHMC_B200_LIB") or os.path.join(HERE, "libmjhmc_b200.so")
 
 F32, F64 = 0, 1
 DIST_TEST_GAUSSIAN, DIST_DIAG_GAUSSIAN, DIST_ROUGH_WELL, DIST_FUNNEL, DIST_FUNNEL_LITERAL, \
     DIST_DENSE_GAUSSIAN, DIST_PRODUCT_OF_T = range(7)
 SAMPLER_DISCRETE, SAMPLER_CONTINUOUS_TIME, SAMPLER_MARKOV_JUMP = range(3)
 RNG_PHILOX, RNG_INJECT = 0, 1
-CNT_L, CNT_F, CNT_FL, CNT_R, CNT_E, CNT_DEDX, CNT_FAIL, CNT_SPARE = range(8)
+CNT_L, CNT_F, CNT_FL, CNT_R, CNT_E, CNT_DEDX, CNT_FAIL, CNT_EXEC = range(8)
 N_COUNTERS = 8
 COUNTER_STRIPES = 32
 INT64_MAX = (1 << 63) - 1

@@ -13,8 +13,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-BUILD = os.path.join(HERE, "_build")
-LIB = os.path.join(HERE, "libmjhmc_b200.so")
+BUILD = os.environ.get("MJHMC_B200_BUILD_DIR") or os.path.join(HERE, "_build")
+LIB = os.environ.get("MJHMC_B200_BUILD_OUT") or os.path.join(HERE, "libmjhmc_b200.so")
+EXTRA = os.environ.get("MJHMC_B200_EXTRA_FLAGS", "").split()
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -43,14 +44,14 @@ def _source_digest():
                 with open(os.path.join(root, fn), "rb") as f:
                     h.update(fn.encode())
                     h.update(f.read())
-    h.update(" ".join(FLAGS).encode())
+    h.update(" ".join(FLAGS + EXTRA).encode())
     return h.hexdigest()
 
 
 def _compile(unit):
     name, src, defs = unit
     obj = os.path.join(BUILD, name + ".o")
-    cmd = [NVCC] + FLAGS + defs + ["-c", src, "-o", obj]
+    cmd = [NVCC] + FLAGS + EXTRA + defs + ["-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (name, " ".join(cmd), r.stderr))
@@ -59,7 +60,7 @@ def _compile(unit):
 
 def build(force=False, verbose=True):
     os.makedirs(BUILD, exist_ok=True)
-    stamp = os.path.join(HERE, "libmjhmc_b200.digest")
+    stamp = os.path.splitext(LIB)[0] + ".digest"
     digest = _source_digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
         return LIB

@@ -89,6 +89,7 @@ static int fill_dist(LaunchParams& p, const mjhmc_dist* dist) {
     p.nbasis = dist->nbasis;
     for (int k = 0; k < 4; ++k) p.dp[k] = dist->p[k];
     p.a0 = dist->a0; p.a1 = dist->a1; p.a2 = dist->a2;
+    if (dist->kind == MJHMC_DIST_ROUGH_WELL) fill_roughwell_coef(p.coef, dist->dtype, dist->p[1]);
     return 0;
 }
 
@@ -97,6 +98,8 @@ static DistParams dist_params(const mjhmc_dist* dist) {
     dp.kind = dist->kind; dp.d = dist->ndims; dp.nbasis = dist->nbasis;
     for (int k = 0; k < 4; ++k) dp.p[k] = dist->p[k];
     dp.a0 = dist->a0; dp.a1 = dist->a1; dp.a2 = dist->a2;
+    for (int k = 0; k < 12; ++k) dp.coef[k] = 0.0;
+    if (dist->kind == MJHMC_DIST_ROUGH_WELL) fill_roughwell_coef(dp.coef, dist->dtype, dist->p[1]);
     return dp;
 }
 

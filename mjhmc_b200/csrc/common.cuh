@@ -7,6 +7,14 @@
 #include <math.h>
 #include "../../include/mjhmc_b200.h"
 
+// Once-per-iteration transcendental code (exp/log/sincospi in fp64) is kept out of line so its
+// register needs do not set the occupancy of the leapfrog loop.
+#ifndef MJ_INLINE_COLD
+#define MJ_COLD static __device__ __noinline__
+#else
+#define MJ_COLD static __device__ __forceinline__
+#endif
+
 namespace mjhmc {
 
 constexpr int kMaxRegDims = 16;          // largest ndims with a register-resident fused kernel
@@ -30,6 +38,7 @@ struct LaunchParams {
     const double* Z; const double* U; const double* U0; long long inj_ld;
     // distribution
     double dp[4];
+    double coef[12];                 // distribution-specific constants precomputed on the host (api.cu)
     const void* a0; const void* a1; const void* a2; int nbasis;
 };
 
@@ -90,7 +99,7 @@ __device__ __forceinline__ double draw_coin(const LaunchParams& p, unsigned long
 }
 
 // Box-Muller pair j of particle i, attempt a: normals 2j and 2j+1 (z1 unused when 2j+1 == d).
-__device__ __forceinline__ void normal_pair(const LaunchParams& p, long long i, unsigned long long attempt,
+MJ_COLD void normal_pair(const LaunchParams& p, long long i, unsigned long long attempt,
                                             int j, int d, double& z0, double& z1) {
     if (p.rng_mode == MJHMC_RNG_INJECT) {
         const double* base = p.Z + (attempt * (unsigned long long)d + 2ull * j) * (unsigned long long)p.inj_ld
@@ -136,7 +145,7 @@ struct Decision { unsigned int choice; double dwell; bool fail; };
 
 // MarkovJumpHMC (markov_jump_hmc.py:366-396): choice 0 = L, 1 = F, 2 = R.
 // ediff_l = H - H_L, ediff_flf = H - H_FLF.
-__device__ __forceinline__ Decision decide_mj(const LaunchParams& p, long long i, unsigned long long attempt,
+MJ_COLD Decision decide_mj(const LaunchParams& p, long long i, unsigned long long attempt,
                                               double ediff_l, double ediff_flf) {
     Decision dc; dc.choice = 0; dc.dwell = 0.0; dc.fail = false;
     const double rl = jump_rate(ediff_l);
@@ -154,7 +163,7 @@ __device__ __forceinline__ Decision decide_mj(const LaunchParams& p, long long i
 }
 
 // ContinuousTimeHMC (markov_jump_hmc.py:261-275): choice 0 = F, 1 = FL, 2 = R.
-__device__ __forceinline__ Decision decide_ct(const LaunchParams& p, long long i, unsigned long long attempt,
+MJ_COLD Decision decide_ct(const LaunchParams& p, long long i, unsigned long long attempt,
                                               double ediff_fl) {
     Decision dc; dc.choice = 0; dc.dwell = 0.0; dc.fail = false;
     const double rfl = jump_rate(ediff_fl);
@@ -171,12 +180,12 @@ __device__ __forceinline__ Decision decide_ct(const LaunchParams& p, long long i
 
 // HMCBase / HMC / ControlHMC (markov_jump_hmc.py:106-148): bit0 = FL accepted, bit1 = flipped,
 // bit2 = the batch-wide R coin fired.
-__device__ __forceinline__ Decision decide_discrete(const LaunchParams& p, long long i, unsigned long long attempt,
-                                                    double ediff) {
+MJ_COLD Decision decide_discrete(const LaunchParams& p, long long i, unsigned long long attempt,
+                                 double ediff, bool coin_fired) {
     Decision dc; dc.dwell = 0.0; dc.fail = false;
     const double p_acc = ediff < 0.0 ? exp(ediff) : 1.0;           // leap_prob
     const Uniform3 u = draw_uniforms(p, i, attempt, false);
-    dc.choice = (u.u0 < p_acc ? 1u : 0u) | (u.u1 < p.p_flip ? 2u : 0u) | (draw_coin(p, attempt) < p.p_r ? 4u : 0u);
+    dc.choice = (u.u0 < p_acc ? 1u : 0u) | (u.u1 < p.p_flip ? 2u : 0u) | (coin_fired ? 4u : 0u);
     return dc;
 }
 
@@ -192,27 +201,42 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
     return v;
 }
 
-// Block-reduce NC local counters and add them to this block's counter stripe.
-template <int NC>
-__device__ __forceinline__ void flush_counters(unsigned long long* counters, const unsigned long long (&loc)[NC],
-                                               const int (&slot)[NC]) {
-    __shared__ unsigned long long sm[NC][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+// Block-reduce the six 32-bit local counters {l, f, fl, r, E, exec} (REDUX per warp, shared
+// atomics per CTA) and add them to this CTA's counter stripe.  dEdX = L * E and the executed
+// gradient evaluations = L * exec are formed here (L is constant inside one launch).
+__device__ __forceinline__ void flush_counters(unsigned long long* counters, const unsigned int (&loc)[6],
+                                               unsigned long long L) {
+    __shared__ unsigned int sm[6];
+    if (threadIdx.x < 6) sm[threadIdx.x] = 0u;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        const unsigned long long s = warp_sum(loc[c]);
-        if (lane == 0) sm[c][warp] = s;
+    for (int c = 0; c < 6; ++c) {
+        const unsigned int s = __reduce_add_sync(0xffffffffu, loc[c]);
+        if (lane == 0 && s) atomicAdd(&sm[c], s);
     }
     __syncthreads();
-    if (warp == 0) {
-        unsigned long long* row = counters + (size_t)(blockIdx.x % MJHMC_COUNTER_STRIPES) * MJHMC_N_COUNTERS;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            unsigned long long s = lane < nwarp ? sm[c][lane] : 0ull;
-            s = warp_sum(s);
-            if (lane == 0 && s) atomicAdd(row + slot[c], s);
-        }
+    unsigned long long* row = counters + (size_t)(blockIdx.x % MJHMC_COUNTER_STRIPES) * MJHMC_N_COUNTERS;
+    if (threadIdx.x < 6) {
+        const unsigned long long s = sm[threadIdx.x];
+        const int slot[6] = {MJHMC_CNT_L, MJHMC_CNT_F, MJHMC_CNT_FL, MJHMC_CNT_R, MJHMC_CNT_E, MJHMC_CNT_EXEC};
+        if (s) atomicAdd(row + slot[threadIdx.x], threadIdx.x == 5 ? s * L : s);
+        if (threadIdx.x == 4 && s) atomicAdd(row + MJHMC_CNT_DEDX, s * L);
     }
+}
+
+// Q coefficients of sin(pi f) = f Q(f^2) on f^2 in [0, 1/4] (dists.cuh: scaled_sin_halfturns)
+static const double kSinQ64[9] = {3.14159265358979312e+00, -5.16771278004996937e+00, 2.55016403987730067e+00,
+                                  -5.99264529318944694e-01, 8.21458865731028998e-02, -7.37043050591694362e-03,
+                                  4.66299816189839390e-04, -2.19034970746260181e-05, 7.69782676822419091e-07};
+static const double kSinQ32[5] = {3.14159264007720340e+00, -5.16771007666831483e+00, 2.55007738652891192e+00,
+                                  -5.98290411283427526e-01, 7.76559122760138720e-02};
+
+// Fills LaunchParams::coef for the RoughWell gradient: -(2 pi / scale2) * Q.
+inline void fill_roughwell_coef(double* coef, int dtype, double scale2) {
+    const double c = -2.0 * 3.14159265358979323846 / scale2;
+    if (dtype == MJHMC_F64) for (int j = 0; j < 9; ++j) coef[j] = c * kSinQ64[j];
+    else for (int j = 0; j < 5; ++j) coef[j] = c * kSinQ32[j];
 }
 
 }  // namespace mjhmc

@@ -17,12 +17,58 @@ namespace mjhmc {
 template <typename T> __device__ __forceinline__ T t_sin(T x);
 template <> __device__ __forceinline__ double t_sin<double>(double x) { return sin(x); }
 template <> __device__ __forceinline__ float t_sin<float>(float x) { return sinf(x); }
+template <typename T> __device__ __forceinline__ T t_sinpi(T x);
+template <> __device__ __forceinline__ double t_sinpi<double>(double x) { return sinpi(x); }
+template <> __device__ __forceinline__ float t_sinpi<float>(float x) { return sinpif(x); }
+template <typename T> __device__ __forceinline__ T t_cospi(T x);
+template <> __device__ __forceinline__ double t_cospi<double>(double x) { return cospi(x); }
+template <> __device__ __forceinline__ float t_cospi<float>(float x) { return cospif(x); }
 template <typename T> __device__ __forceinline__ T t_cos(T x);
 template <> __device__ __forceinline__ double t_cos<double>(double x) { return cos(x); }
 template <> __device__ __forceinline__ float t_cos<float>(float x) { return cosf(x); }
 template <typename T> __device__ __forceinline__ T t_exp(T x);
 template <> __device__ __forceinline__ double t_exp<double>(double x) { return exp(x); }
 template <> __device__ __forceinline__ float t_exp<float>(float x) { return expf(x); }
+
+// sin(pi u) for u in half-turns, branch free and table free (the fp64 leapfrog loop of RoughWell is
+// nothing but this function).  k = rint(u) by the magic-number add, f = u - k in [-1/2, 1/2],
+// sin(pi u) = (-1)^k sin(pi f); the parity of k is the low mantissa bit of (u + magic) and is
+// XOR-ed into the sign of f on the integer pipe.  sin(pi f) = f Q(f^2) with Q fitted at Chebyshev
+// nodes on [0, 1/4] (max relative error 3.9e-17 before rounding in fp64, 6.6e-9 in fp32).
+// `c` holds the Q coefficients pre-multiplied by the caller's scale (host side, api.cu), so the
+// return value is scale * sin(pi u).  Valid for |u| < 2^51 (fp64) / 2^22 (fp32); NaN/Inf -> NaN.
+constexpr int kSinCoefF64 = 9, kSinCoefF32 = 5;
+__device__ __forceinline__ double scaled_sin_halfturns(double u, const double* __restrict__ c) {
+    const double magic = 6755399441055744.0;          // 1.5 * 2^52
+    const double y = u + magic;
+    const double f = u - (y - magic);
+    const int sign = __double2loint(y) << 31;
+    const double fs = __hiloint2double(__double2hiint(f) ^ sign, __double2loint(f));
+    const double z = f * f;
+    double q = c[8];
+    q = fma(q, z, c[7]);
+    q = fma(q, z, c[6]);
+    q = fma(q, z, c[5]);
+    q = fma(q, z, c[4]);
+    q = fma(q, z, c[3]);
+    q = fma(q, z, c[2]);
+    q = fma(q, z, c[1]);
+    q = fma(q, z, c[0]);
+    return q * fs;
+}
+__device__ __forceinline__ float scaled_sin_halfturns(float u, const float* __restrict__ c) {
+    const float magic = 12582912.0f;                   // 1.5 * 2^23
+    const float y = u + magic;
+    const float f = u - (y - magic);
+    const float fs = __int_as_float(__float_as_int(f) ^ (__float_as_int(y) << 31));
+    const float z = f * f;
+    float q = c[4];
+    q = fmaf(q, z, c[3]);
+    q = fmaf(q, z, c[2]);
+    q = fmaf(q, z, c[1]);
+    q = fmaf(q, z, c[0]);
+    return q * fs;
+}
 
 template <typename T, int D>
 struct TestGaussianD {
@@ -66,20 +112,26 @@ struct DiagGaussianD {
 template <typename T, int D>
 struct RoughWellD {
     static constexpr int kind = MJHMC_DIST_ROUGH_WELL;
-    T inv_s1sq, inv_2s1sq, c;   // c = 2 pi / scale2
+    static constexpr int kNC = sizeof(T) == 8 ? kSinCoefF64 : kSinCoefF32;
+    T inv_s1sq, inv_2s1sq, c_pi;      // c_pi = 2 / scale2 (argument of sin / cos in half-turns)
+    T sc[kNC];                        // Q coefficients times -2 pi / scale2
     int d;
     __device__ __forceinline__ explicit RoughWellD(const LaunchParams& p)
         : inv_s1sq((T)(1.0 / (p.dp[0] * p.dp[0]))), inv_2s1sq((T)(1.0 / (2.0 * p.dp[0] * p.dp[0]))),
-          c((T)(2.0 * 3.14159265358979323846 / p.dp[1])), d(p.d) {}
-    __device__ __forceinline__ void grad(const T (&x)[D], T (&g)[D]) const {
+          c_pi((T)(2.0 / p.dp[1])), d(p.d) {
 #pragma unroll
-        for (int k = 0; k < D; ++k) g[k] = x[k] * inv_s1sq - t_sin<T>(x[k] * c) * c;
+        for (int j = 0; j < kNC; ++j) sc[j] = (T)p.coef[j];
+    }
+    __device__ __forceinline__ void grad(const T (&x)[D], T (&g)[D]) const {
+        // x/s1^2 - sin(2 pi x / s2) 2 pi / s2, the sine evaluated in half-turns with the factor folded in
+#pragma unroll
+        for (int k = 0; k < D; ++k) g[k] = x[k] * inv_s1sq + scaled_sin_halfturns(x[k] * c_pi, sc);
     }
     __device__ __forceinline__ T energy(const T (&x)[D]) const {
         T s = (T)0;
 #pragma unroll
         for (int k = 0; k < D; ++k)
-            if (k < d) s += x[k] * x[k] * inv_2s1sq + t_cos<T>(x[k] * c);
+            if (k < d) s += x[k] * x[k] * inv_2s1sq + t_cospi<T>(x[k] * c_pi);
         return s;
     }
 };

@@ -18,7 +18,19 @@
 
 namespace mjhmc {
 
-constexpr int kFusedThreads = 128;
+constexpr int kFusedThreads = 128;       // particles per CTA (one thread each)
+
+// Resident CTAs per SM the register allocator must allow (measured on B200, profiles/r1_variants.md):
+// small ndims want occupancy (the leapfrog loop is a latency-bound fp64 chain), large ndims want
+// registers (x, v, g and the proposal are 6*D live values).
+template <typename T, int D>
+__host__ __device__ constexpr int fused_min_blocks() {
+#ifdef MJ_MINBLOCKS_OVERRIDE
+    return MJ_MINBLOCKS_OVERRIDE;
+#else
+    return sizeof(T) == 8 ? (D <= 4 ? 6 : (D <= 10 ? 3 : 2)) : (D <= 4 ? 8 : (D <= 10 ? 6 : 3));
+#endif
+}
 
 template <typename T, int D>
 __device__ __forceinline__ T kinetic(const T (&v)[D]) {
@@ -43,9 +55,20 @@ __device__ __forceinline__ void leapfrog_L(const Dist& dist, T (&x)[D], T (&v)[D
     }
 }
 
+// FLF cache flags (one byte per particle).  bit0 is the reference's cache_active
+// (hmc_state.py:41-44,131-148: set by an L move, cleared by F and R moves).  bit1 says the
+// cached energy is valid; it is also set by an F move, because the FLF state of F z is F L z,
+// whose energy is the H_L just computed for z -- the bitwise-identical trajectory the reference
+// re-integrates at the next iteration (its own commented-out line markov_jump_hmc.py:400-401).
+// The evaluation counters follow bit0, i.e. they count what the reference would evaluate; the
+// trajectories actually integrated are counted separately (MJHMC_CNT_EXEC).
+constexpr unsigned kCacheRef = 1u, kCacheValid = 2u;
+
 template <class Dist, typename T, int D>
-__global__ void __launch_bounds__(kFusedThreads)
+__global__ void __launch_bounds__(kFusedThreads, fused_min_blocks<T, D>())
 fused_sample_kernel(const __grid_constant__ LaunchParams p) {
+    __shared__ int s_coin[2];          // batch-wide R coin of the discrete samplers, one draw per CTA
+
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < p.n;
     const Dist dist(p);
@@ -55,46 +78,56 @@ fused_sample_kernel(const __grid_constant__ LaunchParams p) {
     const int L = p.L;
     const int sampler = p.sampler;
 
-    unsigned long long n_l = 0, n_f = 0, n_fl = 0, n_r = 0, n_E = 0;
+    unsigned int n_l = 0, n_f = 0, n_fl = 0, n_r = 0, n_E = 0, n_exec = 0;
 
-    if (live) {
-        T x[D], v[D], g[D];
+    T x[D], v[D], g[D];
+    {
         const T* Xin = (const T*)p.Xin;
         const T* Vin = (const T*)p.Vin;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            x[k] = (k < d) ? Xin[(long long)k * p.ld + i] : (T)0;
-            v[k] = (k < d) ? Vin[(long long)k * p.ld + i] : (T)0;
+            x[k] = (live && k < d) ? Xin[(long long)k * p.ld + i] : (T)0;
+            v[k] = (live && k < d) ? Vin[(long long)k * p.ld + i] : (T)0;
         }
-        dist.grad(x, g);
-        T EX = dist.energy(x);
-        T EV = kinetic<T, D>(v);
+    }
+    dist.grad(x, g);
+    T EX = dist.energy(x);
+    T EV = kinetic<T, D>(v);
 
-        bool cached = false;
-        T Hc = (T)0;
-        if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
-            cached = p.ca_in[i] != 0;
-            Hc = ((const T*)p.Hc_in)[i];
+    unsigned int cflags = 0;
+    T Hc = (T)0;
+    if (live && sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
+        cflags = p.ca_in[i];
+        Hc = ((const T*)p.Hc_in)[i];
+    }
+    double dwell = 0.0;
+    bool failed = false;
+
+    for (int it = 0; it < p.n_iter; ++it) {
+        const unsigned long long attempt = p.attempt0 + (unsigned long long)it;
+        const bool active = live && !failed;
+        const T H = EX + EV;                                   // hmc_state.py:80-84
+        T xt[D], vt[D], gt[D];
+        T Hflf = Hc;
+        if (sampler == MJHMC_SAMPLER_DISCRETE) {
+            if (threadIdx.x == 0) s_coin[it & 1] = draw_coin(p, attempt) < p.p_r;   // :138
+            __syncthreads();
         }
-        double dwell = 0.0;
 
-        for (int it = 0; it < p.n_iter; ++it) {
-            const unsigned long long attempt = p.attempt0 + (unsigned long long)it;
-            const T H = EX + EV;                                   // hmc_state.py:80-84
-            T xt[D], vt[D], gt[D];
-
+        if (active) {
             // ---- FLF state (hmc_state.py:109-119): only its energy is ever read
-            T Hflf = Hc;
-            if (sampler == MJHMC_SAMPLER_MARKOV_JUMP && !cached) {
+            if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
+                if (!(cflags & kCacheRef)) n_E += 1;           // the reference evaluates it here
+                if (!(cflags & kCacheValid)) {
 #pragma unroll
-                for (int k = 0; k < D; ++k) { xt[k] = x[k]; vt[k] = -v[k]; gt[k] = g[k]; }
-                leapfrog_L<Dist, T, D>(dist, xt, vt, gt, eps, neg_half_eps, L);
-                const T EVf = kinetic<T, D>(vt);
-                const T EXf = dist.energy(xt);
-                Hflf = EXf + EVf;
-                n_E += 1;
+                    for (int k = 0; k < D; ++k) { xt[k] = x[k]; vt[k] = -v[k]; gt[k] = g[k]; }
+                    leapfrog_L<Dist, T, D>(dist, xt, vt, gt, eps, neg_half_eps, L);
+                    const T EVf = kinetic<T, D>(vt);
+                    const T EXf = dist.energy(xt);
+                    Hflf = EXf + EVf;
+                    n_exec += 1;
+                }
             }
-
             // ---- L state (hmc_state.py:93-100)
 #pragma unroll
             for (int k = 0; k < D; ++k) { xt[k] = x[k]; vt[k] = v[k]; gt[k] = g[k]; }
@@ -103,56 +136,61 @@ fused_sample_kernel(const __grid_constant__ LaunchParams p) {
             const T EXl = dist.energy(xt);
             const T Hl = EXl + EVl;
             n_E += 1;
+            n_exec += 1;
 
-            unsigned int choice;
+            unsigned int choice = 0;
             if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
                 const Decision dc = decide_mj(p, i, attempt, (double)(H - Hl), (double)(H - Hflf));
-                if (dc.fail) { report_failure(p, it); break; }
-                choice = dc.choice; dwell = dc.dwell;
-                if (choice == 0) {
-                    Hc = H; cached = true;                          // :399
+                if (dc.fail) { report_failure(p, it); failed = true; }
+                else {
+                    choice = dc.choice; dwell = dc.dwell;
+                    if (choice == 0) {
+                        Hc = H; cflags = kCacheRef | kCacheValid;   // :399
 #pragma unroll
-                    for (int k = 0; k < D; ++k) { x[k] = xt[k]; v[k] = vt[k]; g[k] = gt[k]; }
-                    EX = EXl; EV = EVl;
-                    n_l += 1;
-                } else if (choice == 1) {
+                        for (int k = 0; k < D; ++k) { x[k] = xt[k]; v[k] = vt[k]; g[k] = gt[k]; }
+                        EX = EXl; EV = EVl;
+                        n_l += 1;
+                    } else if (choice == 1) {
 #pragma unroll
-                    for (int k = 0; k < D; ++k) v[k] = -v[k];
-                    cached = false;                                 // :410
-                    n_f += 1;
-                } else {
-                    T z[D];
-                    draw_normals<T, D>(p, i, attempt, d, z);
+                        for (int k = 0; k < D; ++k) v[k] = -v[k];
+                        Hc = Hl; cflags = kCacheValid;              // :410 clears cache_active; FLF(F z) = F L z
+                        n_f += 1;
+                    } else {
+                        T z[D];
+                        draw_normals<T, D>(p, i, attempt, d, z);
 #pragma unroll
-                    for (int k = 0; k < D; ++k) v[k] = v[k] * (T)p.r_keep + z[k] * (T)p.r_mix;   // hmc_state.py:126
-                    EV = kinetic<T, D>(v);
-                    cached = false;                                 // :409
-                    n_r += 1;
+                        for (int k = 0; k < D; ++k) v[k] = v[k] * (T)p.r_keep + z[k] * (T)p.r_mix;   // hmc_state.py:126
+                        EV = kinetic<T, D>(v);
+                        cflags = 0;                                 // :409
+                        n_r += 1;
+                    }
                 }
             } else if (sampler == MJHMC_SAMPLER_CONTINUOUS_TIME) {
                 // proposal is F L z (markov_jump_hmc.py:258)
                 const Decision dc = decide_ct(p, i, attempt, (double)(H - Hl));
-                if (dc.fail) { report_failure(p, it); break; }
-                choice = dc.choice; dwell = dc.dwell;
-                if (choice == 1) {
+                if (dc.fail) { report_failure(p, it); failed = true; }
+                else {
+                    choice = dc.choice; dwell = dc.dwell;
+                    if (choice == 1) {
 #pragma unroll
-                    for (int k = 0; k < D; ++k) { x[k] = xt[k]; v[k] = -vt[k]; g[k] = gt[k]; }
-                    EX = EXl; EV = EVl;
-                    n_fl += 1;
-                } else if (choice == 0) {
+                        for (int k = 0; k < D; ++k) { x[k] = xt[k]; v[k] = -vt[k]; g[k] = gt[k]; }
+                        EX = EXl; EV = EVl;
+                        n_fl += 1;
+                    } else if (choice == 0) {
 #pragma unroll
-                    for (int k = 0; k < D; ++k) v[k] = -v[k];
-                    n_f += 1;
-                } else {
-                    T z[D];
-                    draw_normals<T, D>(p, i, attempt, d, z);
+                        for (int k = 0; k < D; ++k) v[k] = -v[k];
+                        n_f += 1;
+                    } else {
+                        T z[D];
+                        draw_normals<T, D>(p, i, attempt, d, z);
 #pragma unroll
-                    for (int k = 0; k < D; ++k) v[k] = v[k] * (T)p.r_keep + z[k] * (T)p.r_mix;
-                    EV = kinetic<T, D>(v);
-                    n_r += 1;
+                        for (int k = 0; k < D; ++k) v[k] = v[k] * (T)p.r_keep + z[k] * (T)p.r_mix;
+                        EV = kinetic<T, D>(v);
+                        n_r += 1;
+                    }
                 }
             } else {
-                const Decision dc = decide_discrete(p, i, attempt, (double)(H - Hl));
+                const Decision dc = decide_discrete(p, i, attempt, (double)(H - Hl), s_coin[it & 1] != 0);
                 choice = dc.choice;
                 const bool acc = choice & 1u, flip = choice & 2u;
                 if (acc) {
@@ -177,17 +215,21 @@ fused_sample_kernel(const __grid_constant__ LaunchParams p) {
                 n_fl += (acc && !flip);
             }
 
-            // ---- record (markov_jump_hmc.py:169,334)
-            if (p.samples) {
-                T* S = (T*)p.samples + (long long)it * p.s_stride_it + i;
+            if (!failed) {
+                // ---- record (markov_jump_hmc.py:169,334)
+                if (p.samples) {
+                    T* S = (T*)p.samples + (long long)it * p.s_stride_it + i;
 #pragma unroll
-                for (int k = 0; k < D; ++k)
-                    if (k < d) S[(long long)k * p.s_stride_k] = x[k];
+                    for (int k = 0; k < D; ++k)
+                        if (k < d) S[(long long)k * p.s_stride_k] = x[k];
+                }
+                if (p.dwell) p.dwell[(long long)it * p.n + i] = dwell;
+                if (p.choice) p.choice[(long long)it * p.n + i] = (uint8_t)choice;
             }
-            if (p.dwell) p.dwell[(long long)it * p.n + i] = dwell;
-            if (p.choice) p.choice[(long long)it * p.n + i] = (uint8_t)choice;
         }
+    }
 
+    if (live) {
         T* Xout = (T*)p.Xout;
         T* Vout = (T*)p.Vout;
 #pragma unroll
@@ -198,15 +240,14 @@ fused_sample_kernel(const __grid_constant__ LaunchParams p) {
             }
         }
         if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
-            p.ca_out[i] = cached ? 1 : 0;
+            p.ca_out[i] = (uint8_t)cflags;
             ((T*)p.Hc_out)[i] = Hc;
         }
         if (p.dwell_last && sampler != MJHMC_SAMPLER_DISCRETE) p.dwell_last[i] = dwell;
     }
 
-    const unsigned long long loc[6] = {n_l, n_f, n_fl, n_r, n_E, n_E * (unsigned long long)L};
-    const int slot[6] = {MJHMC_CNT_L, MJHMC_CNT_F, MJHMC_CNT_FL, MJHMC_CNT_R, MJHMC_CNT_E, MJHMC_CNT_DEDX};
-    flush_counters<6>(p.counters, loc, slot);
+    const unsigned int loc[6] = {n_l, n_f, n_fl, n_r, n_E, n_exec};
+    flush_counters(p.counters, loc, (unsigned long long)L);
 }
 
 // Host-side launcher for one (Dist, T, D) instantiation.

@@ -31,8 +31,8 @@ __global__ void __launch_bounds__(kThreads) energy_kernel(DistParams dp, const T
         } break;
         case MJHMC_DIST_ROUGH_WELL: {
             const T inv_2s1sq = (T)(1.0 / (2.0 * dp.p[0] * dp.p[0]));
-            const T c = (T)(2.0 * 3.14159265358979323846 / dp.p[1]);
-            for (int k = 0; k < d; ++k) { const T x = X[k * ld + i]; e += x * x * inv_2s1sq + t_cos<T>(x * c); }
+            const T c_pi = (T)(2.0 / dp.p[1]);
+            for (int k = 0; k < d; ++k) { const T x = X[k * ld + i]; e += x * x * inv_2s1sq + t_cospi<T>(x * c_pi); }
         } break;
         case MJHMC_DIST_FUNNEL:
         case MJHMC_DIST_FUNNEL_LITERAL: {
@@ -87,8 +87,10 @@ __global__ void __launch_bounds__(kThreads) gradient_kernel(DistParams dp, const
         } break;
         case MJHMC_DIST_ROUGH_WELL: {
             const T inv_s1sq = (T)(1.0 / (dp.p[0] * dp.p[0]));
-            const T c = (T)(2.0 * 3.14159265358979323846 / dp.p[1]);
-            for (int k = 0; k < d; ++k) { const T x = X[k * ld + i]; G[k * ld + i] = x * inv_s1sq - t_sin<T>(x * c) * c; }
+            const T c_pi = (T)(2.0 / dp.p[1]);
+            T sc[9];
+            for (int j = 0; j < (sizeof(T) == 8 ? 9 : 5); ++j) sc[j] = (T)dp.coef[j];
+            for (int k = 0; k < d; ++k) { const T x = X[k * ld + i]; G[k * ld + i] = x * inv_s1sq + scaled_sin_halfturns(x * c_pi, sc); }
         } break;
         case MJHMC_DIST_FUNNEL:
         case MJHMC_DIST_FUNNEL_LITERAL: {
@@ -177,7 +179,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) transition_kernel(const __grid_constant__ LaunchParams p, FullPtrs cur,
                                                               FullPtrs prop, const T* __restrict__ H_flf) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long n_l = 0, n_f = 0, n_fl = 0, n_r = 0;
+    unsigned int n_l = 0, n_f = 0, n_fl = 0, n_r = 0;
     if (i < p.n) {
         T* X = (T*)cur.X; T* V = (T*)cur.V; T* G = (T*)cur.G; T* EX = (T*)cur.EX; T* EV = (T*)cur.EV;
         const T* Xp = (const T*)prop.X; const T* Vp = (const T*)prop.V; const T* Gp = (const T*)prop.G;
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(kThreads) transition_kernel(const __grid_const
             if (dc.fail) { report_failure(p, 0); failed = true; }
             else {
                 choice = dc.choice; dwell = dc.dwell;
-                if (choice == 0) { Hc[i] = H; ca[i] = 1; take = 1; n_l = 1; }
+                if (choice == 0) { Hc[i] = H; ca[i] = 3; take = 1; n_l = 1; }
                 else if (choice == 1) { flip = true; ca[i] = 0; n_f = 1; }
                 else { refresh = true; ca[i] = 0; n_r = 1; }
             }
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(kThreads) transition_kernel(const __grid_const
                 else { refresh = true; n_r = 1; }
             }
         } else {
-            const Decision dc = decide_discrete(p, i, attempt, (double)(H - Hl));
+            const Decision dc = decide_discrete(p, i, attempt, (double)(H - Hl), draw_coin(p, attempt) < p.p_r);
             choice = dc.choice;
             const bool acc = choice & 1u;
             flip = choice & 2u;
@@ -254,9 +256,8 @@ __global__ void __launch_bounds__(kThreads) transition_kernel(const __grid_const
             if (p.choice) p.choice[i] = (uint8_t)choice;
         }
     }
-    const unsigned long long loc[4] = {n_l, n_f, n_fl, n_r};
-    const int slot[4] = {MJHMC_CNT_L, MJHMC_CNT_F, MJHMC_CNT_FL, MJHMC_CNT_R};
-    flush_counters<4>(p.counters, loc, slot);
+    const unsigned int loc[6] = {n_l, n_f, n_fl, n_r, 0u, 0u};
+    flush_counters(p.counters, loc, 0ull);
 }
 
 // ------------------------------------------------------------------ host launchers

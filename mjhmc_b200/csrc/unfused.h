@@ -7,6 +7,7 @@ namespace mjhmc {
 struct DistParams {
     int kind, d, nbasis;
     double p[4];
+    double coef[12];
     const void *a0, *a1, *a2;
 };
 

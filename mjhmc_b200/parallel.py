@@ -1,0 +1,118 @@
+"""Particle sharding over the GPUs of one box (one process per GPU, torch.distributed).
+
+Particles are independent chains, so the data path has NO collective: rank r owns the
+contiguous block [r*N/G, (r+1)*N/G) of the (ndims, N) arrays and runs the fused sampler kernel on
+it with ``particle_offset`` = its first global index, which keys the Philox stream by the GLOBAL
+particle index -- results do not depend on G.  NCCL (gloo in the CPU tests) is used only for
+  * the int64 operator / evaluation counters          -> all_reduce(SUM)
+  * autocorrelation partial sums (a mean over particles is a sum)  -> all_reduce(SUM) of float64[n_lags]
+  * samples, when the caller wants the full array     -> all_gather
+The batch-wide R coin of the discrete samplers needs no exchange: it is drawn from a
+particle-independent Philox counter, so every rank computes the same coin.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _device, _lib
+
+COUNTER_NAMES = ("l_count", "f_count", "fl_count", "r_count", "E_count", "dEdX_count")
+
+
+def world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def shard_bounds(n_global, rank, world_size):
+    """Contiguous particle block of `rank`: [lo, hi)."""
+    lo = (n_global * rank) // world_size
+    hi = (n_global * (rank + 1)) // world_size
+    return lo, hi
+
+
+def shard_columns(X, rank, world_size):
+    """The (ndims, n_local) block of a global (ndims, N) array owned by `rank` (a copy)."""
+    lo, hi = shard_bounds(X.shape[1], rank, world_size)
+    return np.ascontiguousarray(X[:, lo:hi]), lo
+
+
+def _comm_device(group=None):
+    backend = dist.get_backend(group)
+    return torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+
+
+def local_counters(sampler):
+    d = sampler.distribution
+    return [int(sampler.l_count), int(sampler.f_count), int(sampler.fl_count), int(sampler.r_count),
+            int(d.E_count), int(d.dEdX_count)]
+
+
+def allreduce_counters(sampler_or_list, group=None):
+    """Global (whole particle cloud) counters as a dict; every rank gets the same ints."""
+    vals = sampler_or_list if isinstance(sampler_or_list, (list, tuple)) else local_counters(sampler_or_list)
+    rank, ws = world(group)
+    if ws > 1:
+        t = torch.tensor(vals, dtype=torch.int64, device=_comm_device(group))
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        vals = [int(v) for v in t.tolist()]
+    return dict(zip(COUNTER_NAMES, vals))
+
+
+def allgather_samples(S, group=None):
+    """Local samples (ndims, n_iter, n_local) -> global (ndims, n_iter, N), particle blocks in rank order."""
+    rank, ws = world(group)
+    if ws == 1:
+        return S
+    dev = _comm_device(group)
+    S = S.to(dev).contiguous()
+    sizes = torch.zeros(ws, dtype=torch.int64, device=dev)
+    sizes[rank] = S.shape[2]
+    dist.all_reduce(sizes, group=group)
+    sizes = [int(n) for n in sizes.tolist()]
+    n_max = max(sizes)
+    if S.shape[2] < n_max:                                   # all_gather wants equal shapes: pad the short shards
+        S = torch.cat([S, S.new_zeros((S.shape[0], S.shape[1], n_max - S.shape[2]))], dim=2)
+    parts = [torch.empty_like(S) for _ in range(ws)]
+    dist.all_gather(parts, S.contiguous(), group=group)
+    return torch.cat([p[:, :, :n] for p, n in zip(parts, sizes)], dim=2)
+
+
+def autocorr_partial(S, n_lags=None):
+    """Un-normalised circular autocorrelation sums of the LOCAL particles on the GPU (K7):
+    ac[tau] = sum_{k,i,t} x[k,t,i] x[k,(t+tau) mod T,i];  S is the device tensor (ndims, T, n_local)."""
+    lib = _lib.load()
+    d, T, n = S.shape
+    n_lags = T if n_lags is None else int(n_lags)
+    ac = torch.zeros(n_lags, dtype=torch.float64, device=S.device)
+    _lib.check(lib.mjhmc_autocorr(_device.dtype_code(S.dtype), d, _device.ptr(S), S.stride(0), S.stride(1), n, T,
+                                  n_lags, _device.ptr(ac), _device.stream_ptr(S.device)), "autocorr")
+    return ac
+
+
+def autocorrelation(S, n_lags=None, group=None, partial=None):
+    """fft_autocor of the reference (misc/autocor.py:37-49) over the WHOLE sharded cloud:
+    per-GPU partial sums, one all_reduce of float64[n_lags], normalised by lag 0."""
+    ac = autocorr_partial(S, n_lags) if partial is None else partial
+    rank, ws = world(group)
+    if ws > 1:
+        ac = ac.to(_comm_device(group))
+        dist.all_reduce(ac, op=dist.ReduceOp.SUM, group=group)
+    ac = ac.double().cpu().numpy()
+    return ac / ac[0]
+
+
+def effective_sample_size(ac):
+    """ESS = T / (1 + 2 sum_{tau >= 1}^{first rho < 0} rho_tau) on the fft_autocor curve.
+    The reference defines no ESS (its figure of merit is a fitted decay, search/objective.py:121-185);
+    this is the definition the build reports."""
+    T = len(ac)
+    s = 0.0
+    for tau in range(1, T):
+        if ac[tau] < 0:
+            break
+        s += ac[tau]
+    return T / (1.0 + 2.0 * s)

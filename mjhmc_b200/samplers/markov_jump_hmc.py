@@ -116,6 +116,9 @@ class _Engine(object):
         self.launches = 0
 
     # ---------------------------------------------------------------- helpers
+    def ctx(self):
+        return torch.cuda.device(self.device)
+
     def _stream(self):
         return _device.stream_ptr(self.device)
 
@@ -287,13 +290,13 @@ class _Engine(object):
     def download(self):
         c = self.cur
         return (self.X[c].double().cpu().numpy(), self.V[c].double().cpu().numpy(),
-                self.ca[c].cpu().numpy().astype(bool), self.Hc[c].double().cpu().numpy())
+                (self.ca[c].cpu().numpy() & 1).astype(bool), self.Hc[c].double().cpu().numpy())
 
     def upload(self, st):
         c = self.cur
         self.X[c].copy_(_device.to_device(st.X, self.dtype, self.device))
         self.V[c].copy_(_device.to_device(st.V, self.dtype, self.device))
-        self.ca[c].copy_(torch.as_tensor(np.asarray(st.cache_active, dtype=np.uint8), device=self.device))
+        self.ca[c].copy_(torch.as_tensor(np.asarray(st.cache_active, dtype=np.uint8) * 3, device=self.device))
         self.Hc[c].copy_(_device.to_device(st.H_cache, self.dtype, self.device))
         if not self.fused:
             self.G = self._callback(self.X[0], True, count=False)
@@ -319,6 +322,9 @@ class HMCBase(object):
         self._engine = None
         self._host_state = None
         self._attempt = 0
+        # B200 extension: gradient evaluations the device actually executed (<= dEdX_count, which
+        # keeps the reference's accounting even where an FLF energy comes from the cache)
+        self.grad_evals_executed = 0
         # do not execute this block if I am an instance of MarkovJumpHMC (markov_jump_hmc.py:46)
         if not isinstance(self, MarkovJumpHMC):
             if isinstance(distribution, Distribution):
@@ -432,6 +438,7 @@ class HMCBase(object):
         if self._engine.fused:
             self.distribution.E_count += cnt[_lib.CNT_E]
             self.distribution.dEdX_count += cnt[_lib.CNT_DEDX]
+            self.grad_evals_executed += cnt[_lib.CNT_EXEC]
 
     def _run(self, n, samples=None, it0=0, dwell=None, choice=None):
         """n sampling iterations, incl. the infinite-rate protocol (markov_jump_hmc.py:364-389)."""
@@ -473,7 +480,7 @@ class HMCBase(object):
         eng = self._engine
         self._sync_state_to_device()
         samples = dwell = choice = None
-        with torch.cuda.device(eng.device):
+        with eng.ctx():
             if record:
                 samples = torch.empty((self.ndims, n, self.nbatch), dtype=eng.tdtype, device=eng.device)
             if want_dwell:
@@ -597,7 +604,7 @@ class ContinuousTimeHMC(HMCBase):
         dwell_t = dwell[:n].reshape(-1)
         total_t = np.sum(dwell_t.cpu().numpy())
         r = np.sort(np.random.random(m)) * total_t
-        with torch.cuda.device(eng.device):
+        with eng.ctx():
             r_d = torch.as_tensor(r, device=eng.device)
             out = torch.zeros((d, m), dtype=eng.tdtype, device=eng.device)
             nbytes = int(eng.lib.mjhmc_resample_scratch_bytes(m))

@@ -301,7 +301,8 @@ def derive_hyperparameters(kind, epsilon=1e-4, alpha=0.2, beta=None, num_leapfro
     if kind == "HMC":
         p_flip = 1
     elif kind in ("ControlHMC", "ContinuousTimeHMC", "MarkovJumpHMC"):
-        p_flip = 1
+        if kind == "ControlHMC":
+            p_flip = 1          # the jump samplers never read p_flip and keep the base value
         with np.errstate(divide='ignore'):
             p_r = - np.log(1 - beta) * 0.5
         beta = 1
