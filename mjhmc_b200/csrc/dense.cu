@@ -1,6 +1,433 @@
-// K4 placeholder translation unit: filled in by the dense-contraction kernels.
+// K4: fused sampler for the dense-contraction energies, fp64 tensor-core (DMMA) path.
+//
+//   full-covariance Gaussian  misc/distributions.py:268-273   dEdX = S X,  E = x.(S x)/2,  S = (J + J^T)/2
+//   ProductOfT                misc/distributions.py:420-433   Y = W^T X + b, E = sum_j (nu_j+1)/2 log(1 + (y_j/nu_j)^2)
+//                             (+ hand-derived autodiff of :431) G_j = (nu_j+1) y_j / (nu_j^2 + y_j^2), dEdX = W G
+//
+// Work decomposition: ONE WARP OWNS 8 PARTICLES for the whole launch.  The gradient of its 8
+// particles is a (rows x K) . (K x 8) product issued as mma.sync.m8n8k4.f64 with the matrix
+// (S, or W^T then W) as the A operand from shared memory (staged once per CTA, read by every
+// warp) and the warp's own 8 positions as the B operand from a warp-private shared tile.  The
+// accumulator layout of the MMA gives every lane a fixed set of (dimension, particle) elements:
+// the momentum of exactly those elements lives in that lane's registers across the L leapfrog
+// steps, the gradient arrives in the same registers as the MMA result, and the position goes
+// through the warp-private tile (written by its owner lane, read as the next B operand).  Warps
+// never synchronise with each other inside the sampling loop (only __syncwarp).
+//
+// The particle state (X, V) stays in HBM between iterations of one launch and is re-read at the
+// start of every trajectory: at L = 10..25 the kernel does 2 d^2 L flops per 5 d S bytes
+// (50..125 flop/B in fp64) -- far above the fp64 machine balance, so the bound is the fp64
+// tensor pipe, not HBM.
 #include "dense.h"
+
 namespace mjhmc {
-bool dense_supported(int, int, int, int) { return false; }
-cudaError_t launch_dense(int, int, const LaunchParams&, cudaStream_t) { return cudaErrorNotSupported; }
+
+constexpr int kDenseMaxWarps = 8;
+constexpr int kDenseThreads = kDenseMaxWarps * 32;   // upper bound; the launcher picks the warp count that fits smem
+constexpr int kCols = 8;                         // particles per warp (N of the MMA)
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
+
+__host__ __device__ inline int dense_ld(int kpad) {          // row stride (doubles) == 4 mod 8: conflict-free A loads
+    int ld = kpad;
+    while ((ld & 7) != 4) ++ld;
+    return ld;
+}
+
+// sum over the 8 lanes that share lane%4 (i.e. over the rows of an accumulator column pair)
+__device__ __forceinline__ double col_sum(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
+}
+
+// value of particle column `c` (0..7) from the per-lane column-pair sums {s0, s1}
+__device__ __forceinline__ double col_pick(double s0, double s1, int c) {
+    const double a = __shfl_sync(0xffffffffu, s0, c >> 1);
+    const double b = __shfl_sync(0xffffffffu, s1, c >> 1);
+    return (c & 1) ? b : a;
+}
+
+struct DenseShared {
+    double* A1;     // [8*MT][ld]  Gaussian: S.  ProductOfT: W^T (rows = experts)
+    double* A2;     // ProductOfT: W (rows = dims)
+    double* nu;     // ProductOfT [8*MT]
+    double* bias;   // ProductOfT [8*MT]
+    double* Xw;     // warp-private [kpad][8]
+    double* Yw;     // ProductOfT warp-private [kpad][8]
+};
+
+// acc[mt] (+)= A[rows 8mt.., :] . B   for this warp's 8 columns; B tile is [kpad][8]
+template <int MT>
+__device__ __forceinline__ void warp_gemm(const double* __restrict__ A, int ld, const double* __restrict__ B,
+                                          int ksteps, double (&acc)[MT][2]) {
+    const int lane = threadIdx.x & 31;
+    const int ar = lane >> 2, ac = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) { acc[mt][0] = 0.0; acc[mt][1] = 0.0; }
+    const double* a_ptr = A + ar * ld + ac;
+    const double* b_ptr = B + ac * kCols + ar;
+    for (int kk = 0; kk < ksteps; ++kk) {
+        const double b = b_ptr[kk * 4 * kCols];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) dmma(acc[mt], a_ptr[(mt * 8) * ld + kk * 4], b);
+    }
+}
+
+template <int MT, bool POT>
+__global__ void __launch_bounds__(kDenseThreads, 1)
+dense_sample_kernel(const __grid_constant__ LaunchParams p) {
+    extern __shared__ double smem[];
+    const int d = p.d;
+    const int rows = 8 * MT;                       // padded dims (== padded experts for ProductOfT)
+    const int kpad = (d + 3) & ~3;
+    const int ksteps = kpad >> 2;
+    const int ld = dense_ld(kpad);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ar = lane >> 2, q = lane & 3;        // accumulator row within a tile, column pair
+
+    DenseShared sh;
+    sh.A1 = smem;
+    double* cur = sh.A1 + rows * ld;
+    sh.A2 = nullptr; sh.nu = nullptr; sh.bias = nullptr; sh.Yw = nullptr;
+    if (POT) {
+        sh.A2 = cur; cur += rows * ld;
+        sh.nu = cur; cur += rows;
+        sh.bias = cur; cur += rows;
+    }
+    sh.Xw = cur + warp * (POT ? 2 : 1) * rows * kCols;
+    if (POT) sh.Yw = sh.Xw + rows * kCols;
+
+    // ---- stage the matrices once per CTA (zero padded)
+    if (POT) {
+        const double* W = (const double*)p.a0;      // [d][nb], nb == d
+        const double* nu = (const double*)p.a1;
+        const double* b = (const double*)p.a2;
+        for (int idx = threadIdx.x; idx < rows * ld; idx += blockDim.x) {
+            const int r = idx / ld, c = idx - r * ld;
+            sh.A1[idx] = (r < d && c < d) ? W[c * d + r] : 0.0;      // W^T
+            sh.A2[idx] = (r < d && c < d) ? W[r * d + c] : 0.0;      // W
+        }
+        for (int idx = threadIdx.x; idx < rows; idx += blockDim.x) {
+            sh.nu[idx] = idx < d ? nu[idx] : 1.0;
+            sh.bias[idx] = idx < d ? b[idx] : 0.0;
+        }
+    } else {
+        const double* S = (const double*)p.a0;      // [d][d]
+        for (int idx = threadIdx.x; idx < rows * ld; idx += blockDim.x) {
+            const int r = idx / ld, c = idx - r * ld;
+            sh.A1[idx] = (r < d && c < d) ? S[r * d + c] : 0.0;
+        }
+    }
+    for (int idx = lane; idx < (POT ? 2 : 1) * rows * kCols; idx += 32) sh.Xw[idx] = 0.0;
+    __syncthreads();
+
+    const int nwarps = blockDim.x >> 5;
+    const long long i0 = ((long long)blockIdx.x * nwarps + warp) * kCols;         // first particle of this warp
+    const long long ic = i0 + 2 * q;                                              // this lane's column pair
+    const bool colv[2] = {ic < p.n, ic + 1 < p.n};
+    const double eps = p.eps, nhe = -p.eps / 2.0;
+    const int L = p.L, sampler = p.sampler;
+
+    // per-particle bookkeeping lives in lanes 0..7 (lane c <-> particle i0 + c)
+    const long long ip = i0 + lane;
+    const bool plive = lane < kCols && ip < p.n;
+    unsigned int cflags = 0;
+    double Hc = 0.0, dwell = 0.0;
+    bool failed = false;
+    if (plive && sampler == MJHMC_SAMPLER_MARKOV_JUMP) { cflags = p.ca_in[ip]; Hc = ((const double*)p.Hc_in)[ip]; }
+    unsigned int n_l = 0, n_f = 0, n_fl = 0, n_r = 0, n_E = 0, n_exec = 0;
+
+    double v[MT][2], g[MT][2];
+
+    // gradient of the positions in Xw -> g; returns nothing.  ProductOfT goes through Yw.
+    auto gradient = [&]() {
+        if (POT) {
+            double y[MT][2];
+            warp_gemm<MT>(sh.A1, ld, sh.Xw, ksteps, y);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int j = mt * 8 + ar;
+                const double nu = sh.nu[j], b = sh.bias[j];
+                double2 o;
+                const double y0 = y[mt][0] + b, y1 = y[mt][1] + b;
+                o.x = j < d ? (nu + 1.0) * y0 / (nu * nu + y0 * y0) : 0.0;
+                o.y = j < d ? (nu + 1.0) * y1 / (nu * nu + y1 * y1) : 0.0;
+                *reinterpret_cast<double2*>(sh.Yw + j * kCols + 2 * q) = o;
+            }
+            __syncwarp();
+            warp_gemm<MT>(sh.A2, ld, sh.Yw, ksteps, g);
+        } else {
+            warp_gemm<MT>(sh.A1, ld, sh.Xw, ksteps, g);
+        }
+        __syncwarp();
+    };
+
+    // energy of the positions in Xw given their gradient g (Gaussian) / via one more W^T X (ProductOfT)
+    auto energy = [&](double& e0, double& e1) {
+        e0 = 0.0; e1 = 0.0;
+        if (POT) {
+            double y[MT][2];
+            warp_gemm<MT>(sh.A1, ld, sh.Xw, ksteps, y);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int j = mt * 8 + ar;
+                if (j < d) {
+                    const double nu = sh.nu[j], b = sh.bias[j], alpha = (nu + 1.0) * 0.5;
+                    const double r0 = (y[mt][0] + b) / nu, r1 = (y[mt][1] + b) / nu;
+                    e0 += alpha * log(1.0 + r0 * r0);
+                    e1 += alpha * log(1.0 + r1 * r1);
+                }
+            }
+            __syncwarp();
+        } else {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const double2 x = *reinterpret_cast<const double2*>(sh.Xw + (mt * 8 + ar) * kCols + 2 * q);
+                e0 += x.x * g[mt][0];
+                e1 += x.y * g[mt][1];
+            }
+            e0 *= 0.5; e1 *= 0.5;
+        }
+        e0 = col_sum(e0); e1 = col_sum(e1);
+    };
+
+    auto kinetic2 = [&](double& k0, double& k1) {
+        k0 = 0.0; k1 = 0.0;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) { k0 += v[mt][0] * v[mt][0]; k1 += v[mt][1] * v[mt][1]; }
+        k0 = col_sum(k0) * 0.5; k1 = col_sum(k1) * 0.5;
+    };
+
+    // load (x, sign * v) of this warp's particles from the state arrays
+    auto load_state = [&](const double* X, const double* V, double sign) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const int r = mt * 8 + ar;
+            double2 x = make_double2(0.0, 0.0);
+            v[mt][0] = 0.0; v[mt][1] = 0.0;
+            if (r < d) {
+                if (colv[0]) { x.x = X[(long long)r * p.ld + ic]; v[mt][0] = sign * V[(long long)r * p.ld + ic]; }
+                if (colv[1]) { x.y = X[(long long)r * p.ld + ic + 1]; v[mt][1] = sign * V[(long long)r * p.ld + ic + 1]; }
+            }
+            *reinterpret_cast<double2*>(sh.Xw + r * kCols + 2 * q) = x;
+        }
+        __syncwarp();
+    };
+
+    // hmc_state.py:86-100 on the warp's 8 particles; g must hold dEdX(Xw) on entry
+    auto leapfrog_L = [&]() {
+        for (int s = 0; s < L; ++s) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                v[mt][0] += nhe * g[mt][0];
+                v[mt][1] += nhe * g[mt][1];
+                double2* xp = reinterpret_cast<double2*>(sh.Xw + (mt * 8 + ar) * kCols + 2 * q);
+                double2 x = *xp;
+                x.x += eps * v[mt][0];
+                x.y += eps * v[mt][1];
+                *xp = x;
+            }
+            __syncwarp();
+            gradient();
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) { v[mt][0] += nhe * g[mt][0]; v[mt][1] += nhe * g[mt][1]; }
+        }
+    };
+
+    for (int it = 0; it < p.n_iter; ++it) {
+        const unsigned long long attempt = p.attempt0 + (unsigned long long)it;
+        const double* Xc = (const double*)(it == 0 ? p.Xin : p.Xout);
+        const double* Vc = (const double*)(it == 0 ? p.Vin : p.Vout);
+        double* Xo = (double*)p.Xout;
+        double* Vo = (double*)p.Vout;
+        const bool active = plive && !failed;
+
+        // ---- FLF energy where the cache does not hold it (hmc_state.py:109-119)
+        double Hflf = Hc;
+        if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
+            const bool need = active && !(cflags & 2u);
+            if (active && !(cflags & 1u)) n_E += 1;
+            if (__any_sync(0xffffffffu, need)) {
+                load_state(Xc, Vc, -1.0);
+                gradient();
+                leapfrog_L();
+                double k0, k1, e0, e1;
+                kinetic2(k0, k1);
+                energy(e0, e1);
+                const double h = col_pick(e0 + k0, e1 + k1, lane & 7);
+                if (need) { Hflf = h; n_exec += 1; }
+            }
+        }
+
+        // ---- current energy and the L proposal (hmc_state.py:93-100)
+        load_state(Xc, Vc, 1.0);
+        gradient();
+        double k0, k1, e0, e1;
+        kinetic2(k0, k1);
+        energy(e0, e1);
+        const double H = col_pick(e0 + k0, e1 + k1, lane & 7);          // EX + EV, hmc_state.py:80-84
+        leapfrog_L();
+        kinetic2(k0, k1);
+        energy(e0, e1);
+        const double Hl = col_pick(e0 + k0, e1 + k1, lane & 7);
+        if (active) { n_E += 1; n_exec += 1; }
+
+        // ---- decision per particle (lanes 0..7)
+        unsigned int coin = 0;
+        if (sampler == MJHMC_SAMPLER_DISCRETE) {
+            if (lane == 0) coin = draw_coin(p, attempt) < p.p_r;
+            coin = __shfl_sync(0xffffffffu, coin, 0);
+        }
+        // take: 0 keep, 1 proposal, 2 proposal with flipped momentum; flip / refresh of the resulting momentum
+        unsigned int take = 0, flip = 0, refresh = 0, choice = 0;
+        if (active) {
+            if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
+                const Decision dc = decide_mj(p, ip, attempt, H - Hl, H - Hflf);
+                if (dc.fail) { report_failure(p, it); failed = true; }
+                else {
+                    choice = dc.choice; dwell = dc.dwell;
+                    if (choice == 0) { take = 1; Hc = H; cflags = 3u; n_l += 1; }
+                    else if (choice == 1) { flip = 1; Hc = Hl; cflags = 2u; n_f += 1; }
+                    else { refresh = 1; cflags = 0u; n_r += 1; }
+                }
+            } else if (sampler == MJHMC_SAMPLER_CONTINUOUS_TIME) {
+                const Decision dc = decide_ct(p, ip, attempt, H - Hl);
+                if (dc.fail) { report_failure(p, it); failed = true; }
+                else {
+                    choice = dc.choice; dwell = dc.dwell;
+                    if (choice == 1) { take = 2; n_fl += 1; }
+                    else if (choice == 0) { flip = 1; n_f += 1; }
+                    else { refresh = 1; n_r += 1; }
+                }
+            } else {
+                const Decision dc = decide_discrete(p, ip, attempt, H - Hl, coin != 0);
+                choice = dc.choice;
+                const bool acc = choice & 1u, fl = choice & 2u;
+                if (acc) take = 2;
+                flip = fl; refresh = (choice & 4u) ? 1u : 0u;
+                n_l += (acc && fl); n_f += (fl && !acc); n_fl += (acc && !fl); n_r += refresh;
+            }
+        }
+        const unsigned int ok = (active && !failed) ? 1u : 0u;
+        const unsigned int code = take | (flip << 2) | (refresh << 3) | (ok << 4);
+
+        // ---- apply to this lane's column pair
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const unsigned int cd = __shfl_sync(0xffffffffu, code, 2 * q + e);
+            const long long i = ic + e;
+            if (!colv[e]) continue;
+            const unsigned int tk = cd & 3u, fp = (cd >> 2) & 1u, rf = (cd >> 3) & 1u, okc = (cd >> 4) & 1u;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int r = mt * 8 + ar;
+                if (r >= d) continue;
+                const long long o = (long long)r * p.ld + i;
+                double xn, vn;
+                if (okc && tk) {
+                    xn = sh.Xw[r * kCols + 2 * q + e];
+                    vn = tk == 1 ? v[mt][e] : -v[mt][e];
+                } else {
+                    xn = Xc[o];
+                    vn = Vc[o];
+                }
+                if (okc && fp) vn = -vn;
+                if (okc && rf) {
+                    double z0, z1;
+                    normal_pair(p, i, attempt, r >> 1, d, z0, z1);
+                    vn = vn * p.r_keep + ((r & 1) ? z1 : z0) * p.r_mix;        // hmc_state.py:126
+                }
+                Xo[o] = xn;
+                Vo[o] = vn;
+                if (okc && p.samples) ((double*)p.samples)[(long long)r * p.s_stride_k + (long long)it * p.s_stride_it + i] = xn;
+            }
+        }
+        if (active && !failed) {
+            if (p.dwell) p.dwell[(long long)it * p.n + ip] = dwell;
+            if (p.choice) p.choice[(long long)it * p.n + ip] = (uint8_t)choice;
+        }
+        __syncwarp();
+    }
+
+    if (plive) {
+        if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) { p.ca_out[ip] = (uint8_t)cflags; ((double*)p.Hc_out)[ip] = Hc; }
+        if (p.dwell_last && sampler != MJHMC_SAMPLER_DISCRETE) p.dwell_last[ip] = dwell;
+    }
+    if (p.n_iter == 0) {
+        // nothing ran: the state still has to reach the output buffers
+        load_state((const double*)p.Xin, (const double*)p.Vin, 1.0);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            if (!colv[e]) continue;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int r = mt * 8 + ar;
+                if (r >= d) continue;
+                ((double*)p.Xout)[(long long)r * p.ld + ic + e] = sh.Xw[r * kCols + 2 * q + e];
+                ((double*)p.Vout)[(long long)r * p.ld + ic + e] = v[mt][e];
+            }
+        }
+    }
+    const unsigned int loc[6] = {n_l, n_f, n_fl, n_r, n_E, n_exec};
+    flush_counters(p.counters, loc, (unsigned long long)L);
+}
+
+static size_t dense_smem_bytes(int MT, int d, bool pot, int nwarps) {
+    const int rows = 8 * MT, kpad = (d + 3) & ~3, ld = dense_ld(kpad);
+    size_t doubles = (size_t)rows * ld * (pot ? 2 : 1) + (pot ? 2 * rows : 0) +
+                     (size_t)nwarps * (pot ? 2 : 1) * rows * kCols;
+    return doubles * sizeof(double);
+}
+
+// most warps per CTA (one CTA per SM) whose tiles fit next to the staged matrices
+static int dense_warps(int MT, int d, bool pot) {
+    for (int nw = kDenseMaxWarps; nw >= 2; nw -= 2)
+        if (dense_smem_bytes(MT, d, pot, nw) <= 227 * 1024) return nw;
+    return 0;
+}
+
+static int dense_mt(int d) {
+    if (d <= 32) return 4;
+    if (d <= 56) return 7;
+    if (d <= 104) return 13;
+    return 0;
+}
+
+bool dense_supported(int dtype, int kind, int ndims, int nbasis) {
+    if (dtype != MJHMC_F64) return false;                      // fp32 states: see DESIGN.md "Dense path"
+    if (kind == MJHMC_DIST_PRODUCT_OF_T && nbasis != ndims) return false;
+    const int mt = dense_mt(ndims);
+    if (!mt) return false;
+    return dense_warps(mt, ndims, kind == MJHMC_DIST_PRODUCT_OF_T) > 0;
+}
+
+template <int MT, bool POT>
+static cudaError_t launch_dense_T(const LaunchParams& p, cudaStream_t stream) {
+    const int nwarps = dense_warps(MT, p.d, POT);
+    if (!nwarps) return cudaErrorNotSupported;
+    const size_t smem = dense_smem_bytes(MT, p.d, POT, nwarps);
+    cudaError_t e = cudaFuncSetAttribute(dense_sample_kernel<MT, POT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long per_cta = (long long)nwarps * kCols;
+    const long long blocks = (p.n + per_cta - 1) / per_cta;
+    dense_sample_kernel<MT, POT><<<(unsigned)blocks, nwarps * 32, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dense(int dtype, int kind, const LaunchParams& p, cudaStream_t stream) {
+    if (dtype != MJHMC_F64) return cudaErrorNotSupported;
+    const bool pot = kind == MJHMC_DIST_PRODUCT_OF_T;
+    switch (dense_mt(p.d)) {
+        case 4:  return pot ? launch_dense_T<4, true>(p, stream) : launch_dense_T<4, false>(p, stream);
+        case 7:  return pot ? launch_dense_T<7, true>(p, stream) : launch_dense_T<7, false>(p, stream);
+        case 13: return pot ? launch_dense_T<13, true>(p, stream) : launch_dense_T<13, false>(p, stream);
+        default: return cudaErrorNotSupported;
+    }
+}
+
+}  // namespace mjhmc

@@ -91,6 +91,8 @@ class Distribution(object):
 
 class _DeviceEnergy(Distribution):
     """Built-in energies: E_val / dEdX_val run the stand-alone device kernels."""
+    # the unfused sampler path may hand device tensors straight to E / dEdX
+    accepts_device_arrays = True
 
     def _eval(self, X, want_grad):
         lib = _lib.load()

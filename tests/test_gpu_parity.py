@@ -191,3 +191,68 @@ def test_energy_gradient_kernels_match_oracle():
         assert (dist.E_count - e0, dist.dEdX_count - g0) == (33, 33)
         assert helpers.rel_err(E[0], energy.E(X)) < 1e-12, type(dist).__name__
         assert helpers.rel_err(G, energy.dEdX(X)) < 1e-12, type(dist).__name__
+
+
+def _dense_case(dist_name, d, N, rs):
+    from mjhmc_b200.misc import distributions as D
+    if dist_name == "Gaussian":
+        dist = D.Gaussian.rotated(ndims=d, nbatch=N, log_conditioning=2, seed=d)
+        energy = orc.GaussianEnergy(dist.J)
+        X0 = dist.Xinit.copy()
+    else:
+        W = (rs.randn(d, d) / np.sqrt(d)).astype(np.float32)
+        nu = (rs.rand(d) * 2 + 2.1).astype(np.float32)
+        b = (rs.randn(d) * 0.1).astype(np.float32)
+        dist = D.ProductOfT(ndims=d, nbasis=d, nbatch=N, W=W, lognu=np.log(nu.astype(np.float64)), b=b)
+        energy = orc.ProductOfTEnergy(dist.weights, dist.nu, dist.bias)
+        X0 = rs.randn(d, N)
+    return dist, energy, X0
+
+
+@pytest.mark.parametrize("kind", orc.KINDS)
+@pytest.mark.parametrize("dist_name,d", [("Gaussian", 5), ("Gaussian", 40), ("Gaussian", 100),
+                                         ("ProductOfT", 6), ("ProductOfT", 36), ("ProductOfT", 100)])
+def test_dense_kernel_matches_oracle(kind, dist_name, d):
+    """K4 (DMMA): full-covariance Gaussian and ProductOfT, PHILOX mode, all sampler classes,
+    particle counts that are not multiples of the warp / CTA tile."""
+    from mjhmc_b200.samplers import markov_jump_hmc as S
+    rs = np.random.RandomState(1000 + d)
+    N = 77 if d < 100 else 150
+    dist, energy, X0 = _dense_case(dist_name, d, N, rs)
+    V0 = rs.randn(d, N)
+    helpers.pin_init(dist, X0)
+    hp = dict(epsilon=0.15, beta=0.3, num_leapfrog_steps=4)
+    extra = dict(resample=False) if kind in ("ContinuousTimeHMC", "MarkovJumpHMC") else {}
+    seed, offset = 4242 + d, 64
+    s = getattr(S, kind)(distribution=dist, V=V0, seed=seed, particle_offset=offset, **hp, **extra)
+    assert s._engine.fused
+    o = orc.OracleSampler(kind, energy, X0, V=V0, draws=orc.PhiloxDraws(seed, offset), resample=False, **hp)
+    n = 5
+    X = s.sample(n)
+    Xo = o.sample(n)
+    assert helpers.rel_err(X, Xo) < 1e-9, (kind, dist_name, d)
+    assert helpers.rel_err(s.state.V, o.V) < 1e-9
+    c = o.counters()
+    assert _counters(s, dist) == [c["l"], c["f"], c["fl"], c["r"], c["E"], c["dEdX"]]
+    if kind in ("ContinuousTimeHMC", "MarkovJumpHMC"):
+        fin = np.isfinite(o.dwelling_times)
+        assert helpers.rel_err(s.dwelling_times[fin], o.dwelling_times[fin]) < 1e-8
+    assert s._engine.launches == 1
+
+
+def test_dense_float32_state_uses_unfused_device_path():
+    """fp32 states have no fused dense kernel yet: the sampler must still run on the GPU (unfused
+    pieces + device gradient kernels) and agree with the fp64 oracle to fp32 accuracy."""
+    from mjhmc_b200.samplers import markov_jump_hmc as S
+    rs = np.random.RandomState(5)
+    dist, energy, X0 = _dense_case("Gaussian", 12, 40, rs)
+    V0 = rs.randn(12, 40)
+    helpers.pin_init(dist, X0)
+    hp = dict(epsilon=0.1, beta=0.3, num_leapfrog_steps=3)
+    s = S.ControlHMC(distribution=dist, V=V0, seed=3, dtype="float32", **hp)
+    assert not s._engine.fused
+    o = orc.OracleSampler("ControlHMC", energy, X0, V=V0, draws=orc.PhiloxDraws(3), **hp)
+    X, Xo = s.sample(2), o.sample(2)
+    same = np.all(np.abs(X - Xo) <= 1e-3 * (1 + np.abs(Xo)), axis=0)
+    assert same.mean() > 0.95
+    assert helpers.rel_err(X[:, same], Xo[:, same]) < 1e-4
