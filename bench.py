@@ -42,6 +42,13 @@ WORKLOADS = {
                                 source="search/control_rw/params_new.json"),
     "funnel10d_cthmc": dict(dist="Funnel", ndims=10, n=4_000_000, sampler="ContinuousTimeHMC",
                             epsilon=0.1, beta=0.5, L=10, iters=16, source="search/MJHMC_funnel/config.json midpoints"),
+    # configs[2] / configs[3]: dense-contraction energies on the fp64 tensor pipe (DMMA)
+    "gauss100d_mjhmc": dict(dist="GaussianRot", ndims=100, n=1_000_000, sampler="MarkovJumpHMC",
+                            epsilon=1.4581446647644043, beta=0.009999999776482582, L=25, iters=2,
+                            source="search/MJHMC_log_gauss/params_2.json; J = Q^T diag(10**linspace(-6,0,100)) Q"),
+    "pot100d_mjhmc": dict(dist="ProductOfT", ndims=100, n=1_000_000, sampler="MarkovJumpHMC",
+                          epsilon=0.4827975928783417, beta=0.10154356807470322, L=10, iters=2,
+                          source="search/MJHMC_poe_100/params.json; dense W = randn/sqrt(100)"),
     # HBM-bound points of the fused leapfrog (one iteration per launch, L = 1)
     "testgauss2d_control_L1": dict(dist="TestGaussian", ndims=2, n=16_000_000, sampler="ControlHMC",
                                    epsilon=0.5, beta=0.1, L=1, iters=1, source="HBM roofline point"),
@@ -49,6 +56,8 @@ WORKLOADS = {
                                    epsilon=0.5, beta=0.1, L=1, iters=1, source="HBM roofline point"),
 }
 DEFAULT_WORKLOAD = "roughwell2d_mjhmc"
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full captures (profiles/)
+TRAFFIC = {"roughwell2d_mjhmc": 46034944 + 1041338000}
 DTYPE = "float64"          # the reference's arithmetic
 METRIC = "particle_leapfrog_steps_per_s"
 UNIT = "particle-leapfrog-steps/s"
@@ -86,7 +95,25 @@ def _oracle_energy(w):
         return orc.TestGaussianEnergy(1.0)
     if w["dist"] == "Funnel":
         return orc.FunnelEnergy(3.0)
+    if w["dist"] == "GaussianRot":
+        return orc.GaussianEnergy(_rotated_J(w["ndims"]))
+    if w["dist"] == "ProductOfT":
+        W, nu = _pot_params(w["ndims"])
+        return orc.ProductOfTEnergy(W, nu)
     raise KeyError(w["dist"])
+
+
+def _rotated_J(d, log_conditioning=6, seed=0):
+    cond = 10 ** np.linspace(-log_conditioning, 0, d)
+    Q, _ = np.linalg.qr(np.random.RandomState(seed).randn(d, d))
+    return Q.T.dot(np.diag(cond)).dot(Q)
+
+
+def _pot_params(d, seed=2015):
+    rs = np.random.RandomState(seed)
+    W = (rs.randn(d, d) / np.sqrt(d)).astype(np.float32)
+    nu = (rs.rand(d) * 2 + 2.1).astype(np.float32)
+    return W, nu
 
 
 def _init_cloud(w, n, seed):
@@ -97,6 +124,9 @@ def _init_cloud(w, n, seed):
     elif w["dist"] == "Funnel":
         x0 = rs.normal(scale=3.0, size=(1, n))
         X = np.vstack((x0, rs.normal(scale=np.exp(x0 / 2.), size=(d - 1, n))))
+    elif w["dist"] == "GaussianRot":
+        wv, Q = np.linalg.eigh(_rotated_J(d))
+        X = Q.dot((1. / np.sqrt(wv)).reshape((-1, 1)) * rs.randn(d, n))
     else:
         X = rs.randn(d, n)
     return X, rs.randn(d, n)
@@ -121,7 +151,8 @@ def run_reference(w, steps, warmup, n_sample=None, quiet=False):
     """All host cores: the particle cloud is split over one process per core (chains are independent)."""
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    n_sample = n_sample or 100_000 * cores
+    # about 10-30 s of CPU work: scale the per-core particle count with the dimension
+    n_sample = n_sample or max(1000, 200_000 // w["ndims"]) * cores
     per = max(1, n_sample // cores)
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
@@ -201,8 +232,14 @@ def make_sampler(w, rank, dtype=DTYPE, seed=2024):
         dist = D.TestGaussian(ndims=d, nbatch=n)
     elif w["dist"] == "Funnel":
         dist = D.Funnel(scale=3.0, ndims=d, nbatch=n)
+    elif w["dist"] == "GaussianRot":
+        dist = D.Gaussian(ndims=d, nbatch=8, J=_rotated_J(d))
+    elif w["dist"] == "ProductOfT":
+        W, nu = _pot_params(d)
+        dist = D.ProductOfT(ndims=d, nbasis=d, nbatch=8, W=W, lognu=np.log(nu.astype(np.float64)))
     else:
         raise KeyError(w["dist"])
+    dist.nbatch = n
     X0, V0 = _init_cloud(w, n, 1000 + rank)
     dist.gen_init_X = lambda: setattr(dist, "Xinit", X0)
     kw = dict(resample=False) if w["sampler"] in ("ContinuousTimeHMC", "MarkovJumpHMC") else {}
@@ -273,8 +310,8 @@ def run_b200(args, w):
 
     # ---- e2e: host buffers in, host samples out, through the public API, every step
     from mjhmc_b200.samplers.hmc_state import HMCState
-    Xh = torch.as_tensor(X0).pin_memory().numpy()
-    Vh = torch.as_tensor(V0).pin_memory().numpy()
+    Xh = torch.as_tensor(X0).pin_memory()                  # host inputs live in pinned memory
+    Vh = torch.as_tensor(V0).pin_memory()
     e2e_steps = max(1, min(args.steps, 5))
     barrier()
     g1 = sampler.grad_evals_executed
@@ -303,6 +340,23 @@ def run_b200(args, w):
         alg = algorithmic_bytes_per_launch(w)
         launch_ms = ms_max / args.steps
         achieved = alg / (launch_ms * 1e-3) / 1e9
+        if w["dist"] in ("GaussianRot", "ProductOfT"):
+            # dense-contraction energies: algorithmic flops per leapfrog step = 2 d^2 (S x) resp. 4 d nb (W^T x, W G)
+            fl = (2 if w["dist"] == "GaussianRot" else 4) * w["ndims"] ** 2
+            tf = grads_all * fl / (ms_max * 1e-3) / 1e12 / world
+            roofline = {"bound": "tensor", "achieved": tf, "peak": 40.0, "unit": "TFLOP/s", "frac": tf / 40.0,
+                        "traffic": None, "kernel": "dense_sample_kernel (mma.sync m8n8k4 f64 = DMMA)",
+                        "peak_source": "nominal B200 fp64 tensor-core rate; MEASURED_PEAKS.json has no fp64 figure "
+                                       "(its bf16 cuBLAS number does not apply to an fp64 path)",
+                        "algorithmic_flops_per_leapfrog_step": fl, "launch_ms": launch_ms,
+                        "hbm_gbs": achieved, "note": "ncu sm__pipe_tensor_cycles_active in profiles/r1_dense_*.txt"}
+        else:
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": TRAFFIC.get(args.workload), "peak_source": peak_src, "kernel": "fused_sample_kernel",
+                        "algorithmic_bytes_per_launch": alg, "launch_ms": launch_ms,
+                        "note": ("L=%d leapfrog steps per sample: the kernel is FP64-issue bound "
+                                 "(ncu sm__pipe_fp64_cycles_active 71%%, DESIGN.md 3.1), not HBM bound" % w["L"])
+                        if w["L"] > 4 else "HBM-bound point"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -314,11 +368,7 @@ def run_b200(args, w):
                        "particles_per_gpu": w["n"], "iterations_per_step": iters,
                        "l2": "flushed with a 256 MB fill between timed steps", "rng": "philox4x32-10",
                        "parallelism": "particle shards, dp%d" % world},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "fused_sample_kernel",
-                         "algorithmic_bytes_per_launch": alg, "launch_ms": launch_ms,
-                         "note": "L=%d leapfrog steps of fp64 sin() per sample: the kernel is FP64-issue bound, "
-                                 "see DESIGN.md" % w["L"] if w["L"] > 4 else "HBM-bound point"},
+            "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},

@@ -64,6 +64,8 @@ enum {
 };
 /* the kernels stripe their atomics over this many counter rows; mjhmc_counters_reduce folds them */
 #define MJHMC_COUNTER_STRIPES 32
+/* rows of the counter block: the stripes plus one row of work-queue heads for the persistent kernels */
+#define MJHMC_COUNTER_ROWS (MJHMC_COUNTER_STRIPES + 1)
 
 typedef struct mjhmc_dist {
     int32_t kind;       /* MJHMC_DIST_*  */
@@ -120,7 +122,7 @@ typedef struct mjhmc_outputs {
     double  *dwell_last;        /* (n,): dwelling time of the last iteration -> sampler.dwelling_times */
     uint8_t *choice;            /* (n_iter, n): operator taken; MJ 0=L 1=F 2=R, CT 0=F 1=FL 2=R,
                                    discrete bit0=accepted bit1=flipped bit2=R fired */
-    int64_t *counters;          /* [MJHMC_COUNTER_STRIPES][MJHMC_N_COUNTERS], += */
+    int64_t *counters;          /* [MJHMC_COUNTER_ROWS][MJHMC_N_COUNTERS], +=; reset before every launch */
 } mjhmc_outputs;
 
 const char *mjhmc_last_error(void);

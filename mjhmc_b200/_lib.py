@@ -18,6 +18,7 @@ RNG_PHILOX, RNG_INJECT = 0, 1
 CNT_L, CNT_F, CNT_FL, CNT_R, CNT_E, CNT_DEDX, CNT_FAIL, CNT_EXEC = range(8)
 N_COUNTERS = 8
 COUNTER_STRIPES = 32
+COUNTER_ROWS = COUNTER_STRIPES + 1
 INT64_MAX = (1 << 63) - 1
 ABI_VERSION = 1
 

@@ -233,7 +233,7 @@ int mjhmc_transition(int32_t dtype, int32_t ndims, const mjhmc_hp* hp, const mjh
 
 int mjhmc_counters_reset(int64_t* counters, void* stream_) {
     if (!counters) return fail("NULL argument");
-    int64_t h[MJHMC_COUNTER_STRIPES][MJHMC_N_COUNTERS];
+    int64_t h[MJHMC_COUNTER_ROWS][MJHMC_N_COUNTERS];
     memset(h, 0, sizeof h);
     for (int s = 0; s < MJHMC_COUNTER_STRIPES; ++s) h[s][MJHMC_CNT_FAIL] = INT64_MAX;
     cudaStream_t stream = (cudaStream_t)stream_;

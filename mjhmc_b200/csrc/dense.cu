@@ -31,11 +31,11 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
                  : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-__host__ __device__ inline int dense_ld(int kpad) {          // row stride (doubles) == 4 mod 8: conflict-free A loads
-    int ld = kpad;
-    while ((ld & 7) != 4) ++ld;
-    return ld;
-}
+// Row stride (doubles) of the staged matrices: 8*MT + 4 == 4 (mod 8), so the 8x4 A fragment of
+// mma.m8n8k4 (rows at stride LD, 4 consecutive doubles each) and the transposed 4x8 read of the
+// same matrix both hit every bank exactly twice -- the minimum for a 256-byte warp request.  A
+// compile-time stride turns the per-tile offsets into LDS immediates.
+template <int MT> struct DenseLd { static constexpr int value = 8 * MT + 4; };
 
 // sum over the 8 lanes that share lane%4 (i.e. over the rows of an accumulator column pair)
 __device__ __forceinline__ double col_sum(double v) {
@@ -53,28 +53,33 @@ __device__ __forceinline__ double col_pick(double s0, double s1, int c) {
 }
 
 struct DenseShared {
-    double* A1;     // [8*MT][ld]  Gaussian: S.  ProductOfT: W^T (rows = experts)
-    double* A2;     // ProductOfT: W (rows = dims)
+    double* A1;     // [8*MT][LD]  Gaussian: S.  ProductOfT: W (rows = dims, cols = experts), read both ways
     double* nu;     // ProductOfT [8*MT]
     double* bias;   // ProductOfT [8*MT]
     double* Xw;     // warp-private [kpad][8]
     double* Yw;     // ProductOfT warp-private [kpad][8]
 };
 
-// acc[mt] (+)= A[rows 8mt.., :] . B   for this warp's 8 columns; B tile is [kpad][8]
-template <int MT>
-__device__ __forceinline__ void warp_gemm(const double* __restrict__ A, int ld, const double* __restrict__ B,
+// acc[mt] = M[rows 8mt.., :] . B  (TRANS = false)  or  M^T[rows 8mt.., :] . B  (TRANS = true)
+// for this warp's 8 columns; M is [8*MT][LD] in shared memory, the B tile is [kpad][8].
+template <int MT, bool TRANS>
+__device__ __forceinline__ void warp_gemm(const double* __restrict__ M, const double* __restrict__ B,
                                           int ksteps, double (&acc)[MT][2]) {
+    constexpr int LD = DenseLd<MT>::value;
     const int lane = threadIdx.x & 31;
     const int ar = lane >> 2, ac = lane & 3;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) { acc[mt][0] = 0.0; acc[mt][1] = 0.0; }
-    const double* a_ptr = A + ar * ld + ac;
+    // A fragment element (row 8mt + ar, col 4kk + ac) of M, resp. of M^T = M[4kk + ac][8mt + ar]
+    const double* a_ptr = TRANS ? M + ac * LD + ar : M + ar * LD + ac;
     const double* b_ptr = B + ac * kCols + ar;
+#pragma unroll 1
     for (int kk = 0; kk < ksteps; ++kk) {
-        const double b = b_ptr[kk * 4 * kCols];
+        const double b = *b_ptr;
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) dmma(acc[mt], a_ptr[(mt * 8) * ld + kk * 4], b);
+        for (int mt = 0; mt < MT; ++mt) dmma(acc[mt], TRANS ? a_ptr[mt * 8] : a_ptr[mt * 8 * LD], b);
+        a_ptr += TRANS ? 4 * LD : 4;
+        b_ptr += 4 * kCols;
     }
 }
 
@@ -86,16 +91,15 @@ dense_sample_kernel(const __grid_constant__ LaunchParams p) {
     const int rows = 8 * MT;                       // padded dims (== padded experts for ProductOfT)
     const int kpad = (d + 3) & ~3;
     const int ksteps = kpad >> 2;
-    const int ld = dense_ld(kpad);
+    constexpr int ld = DenseLd<MT>::value;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ar = lane >> 2, q = lane & 3;        // accumulator row within a tile, column pair
 
     DenseShared sh;
     sh.A1 = smem;
     double* cur = sh.A1 + rows * ld;
-    sh.A2 = nullptr; sh.nu = nullptr; sh.bias = nullptr; sh.Yw = nullptr;
+    sh.nu = nullptr; sh.bias = nullptr; sh.Yw = nullptr;
     if (POT) {
-        sh.A2 = cur; cur += rows * ld;
         sh.nu = cur; cur += rows;
         sh.bias = cur; cur += rows;
     }
@@ -109,8 +113,7 @@ dense_sample_kernel(const __grid_constant__ LaunchParams p) {
         const double* b = (const double*)p.a2;
         for (int idx = threadIdx.x; idx < rows * ld; idx += blockDim.x) {
             const int r = idx / ld, c = idx - r * ld;
-            sh.A1[idx] = (r < d && c < d) ? W[c * d + r] : 0.0;      // W^T
-            sh.A2[idx] = (r < d && c < d) ? W[r * d + c] : 0.0;      // W
+            sh.A1[idx] = (r < d && c < d) ? W[r * d + c] : 0.0;
         }
         for (int idx = threadIdx.x; idx < rows; idx += blockDim.x) {
             sh.nu[idx] = idx < d ? nu[idx] : 1.0;
@@ -126,74 +129,81 @@ dense_sample_kernel(const __grid_constant__ LaunchParams p) {
     for (int idx = lane; idx < (POT ? 2 : 1) * rows * kCols; idx += 32) sh.Xw[idx] = 0.0;
     __syncthreads();
 
-    const int nwarps = blockDim.x >> 5;
-    const long long i0 = ((long long)blockIdx.x * nwarps + warp) * kCols;         // first particle of this warp
-    const long long ic = i0 + 2 * q;                                              // this lane's column pair
-    const bool colv[2] = {ic < p.n, ic + 1 < p.n};
     const double eps = p.eps, nhe = -p.eps / 2.0;
     const int L = p.L, sampler = p.sampler;
+    unsigned int n_l = 0, n_f = 0, n_fl = 0, n_r = 0, n_E = 0, n_exec = 0;
 
-    // per-particle bookkeeping lives in lanes 0..7 (lane c <-> particle i0 + c)
-    const long long ip = i0 + lane;
-    const bool plive = lane < kCols && ip < p.n;
+    // Persistent warps: groups of 8 consecutive particles are handed out through an atomic work
+    // head (row MJHMC_COUNTER_STRIPES of the counter block), so a warp whose particles needed an
+    // extra FLF trajectory does not hold back the other seven warps of its SM, and the matrix is
+    // staged once per SM for the whole launch.
+    unsigned long long* work_head = p.counters + (size_t)MJHMC_COUNTER_STRIPES * MJHMC_N_COUNTERS;
+    long long i0 = 0, ic = 0, ip = 0;
+    bool colv[2] = {false, false};
+    bool plive = false;
     unsigned int cflags = 0;
     double Hc = 0.0, dwell = 0.0;
     bool failed = false;
-    if (plive && sampler == MJHMC_SAMPLER_MARKOV_JUMP) { cflags = p.ca_in[ip]; Hc = ((const double*)p.Hc_in)[ip]; }
-    unsigned int n_l = 0, n_f = 0, n_fl = 0, n_r = 0, n_E = 0, n_exec = 0;
 
     double v[MT][2], g[MT][2];
 
-    // gradient of the positions in Xw -> g; returns nothing.  ProductOfT goes through Yw.
-    auto gradient = [&]() {
+    // Gradient of the positions in Xw -> g, and (when want_e) their energy as per-lane column-pair
+    // sums e0, e1.  One call site only: the unrolled MMA sequences are the bulk of the code and the
+    // eight warps of a persistent CTA run out of phase, so every extra copy costs instruction-cache
+    // misses (profiles/r1_dense_pot_v3: 46 % stall_no_inst with five inlined copies).
+    //   Gaussian   : g = S x,  E = x.g / 2
+    //   ProductOfT : y = W^T x + b;  E = sum_j (nu_j+1)/2 log(1 + (y_j/nu_j)^2);  g = W [(nu+1) y / (nu^2 + y^2)]
+    auto gradient = [&](bool want_e, double& e0, double& e1) {
+        e0 = 0.0; e1 = 0.0;
         if (POT) {
             double y[MT][2];
-            warp_gemm<MT>(sh.A1, ld, sh.Xw, ksteps, y);
+            warp_gemm<MT, true>(sh.A1, sh.Xw, ksteps, y);            // Y = W^T X
+            if (want_e) {
+                // energy through a rolled loop over the tile rows (the values take a detour through the
+                // warp's Yw tile) so the two log() expansions exist once, not 2*MT times
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+                    *reinterpret_cast<double2*>(sh.Yw + (mt * 8 + ar) * kCols + 2 * q) = make_double2(y[mt][0], y[mt][1]);
+#pragma unroll 1
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int j = mt * 8 + ar;
+                    if (j < d) {
+                        const double2 yy = *reinterpret_cast<const double2*>(sh.Yw + j * kCols + 2 * q);
+                        const double nu = sh.nu[j], b = sh.bias[j], alpha = (nu + 1.0) * 0.5;
+                        const double r0 = (yy.x + b) / nu, r1 = (yy.y + b) / nu;
+                        e0 += alpha * log(1.0 + r0 * r0);
+                        e1 += alpha * log(1.0 + r1 * r1);
+                    }
+                }
+            }
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 const int j = mt * 8 + ar;
                 const double nu = sh.nu[j], b = sh.bias[j];
-                double2 o;
                 const double y0 = y[mt][0] + b, y1 = y[mt][1] + b;
-                o.x = j < d ? (nu + 1.0) * y0 / (nu * nu + y0 * y0) : 0.0;
-                o.y = j < d ? (nu + 1.0) * y1 / (nu * nu + y1 * y1) : 0.0;
+                // (nu+1) y / (nu^2 + y^2) with a correctly rounded reciprocal (MUFU.RCP64H + Newton) instead of
+                // the full division sequence: <= 1 ulp apart, a third of the code
+                double2 o;
+                o.x = j < d ? (nu + 1.0) * y0 * __drcp_rn(fma(y0, y0, nu * nu)) : 0.0;
+                o.y = j < d ? (nu + 1.0) * y1 * __drcp_rn(fma(y1, y1, nu * nu)) : 0.0;
                 *reinterpret_cast<double2*>(sh.Yw + j * kCols + 2 * q) = o;
             }
             __syncwarp();
-            warp_gemm<MT>(sh.A2, ld, sh.Yw, ksteps, g);
+            warp_gemm<MT, false>(sh.A1, sh.Yw, ksteps, g);          // dEdX = W G
         } else {
-            warp_gemm<MT>(sh.A1, ld, sh.Xw, ksteps, g);
+            warp_gemm<MT, false>(sh.A1, sh.Xw, ksteps, g);
+            if (want_e) {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const double2 x = *reinterpret_cast<const double2*>(sh.Xw + (mt * 8 + ar) * kCols + 2 * q);
+                    e0 += x.x * g[mt][0];
+                    e1 += x.y * g[mt][1];
+                }
+                e0 *= 0.5; e1 *= 0.5;
+            }
         }
         __syncwarp();
-    };
-
-    // energy of the positions in Xw given their gradient g (Gaussian) / via one more W^T X (ProductOfT)
-    auto energy = [&](double& e0, double& e1) {
-        e0 = 0.0; e1 = 0.0;
-        if (POT) {
-            double y[MT][2];
-            warp_gemm<MT>(sh.A1, ld, sh.Xw, ksteps, y);
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                const int j = mt * 8 + ar;
-                if (j < d) {
-                    const double nu = sh.nu[j], b = sh.bias[j], alpha = (nu + 1.0) * 0.5;
-                    const double r0 = (y[mt][0] + b) / nu, r1 = (y[mt][1] + b) / nu;
-                    e0 += alpha * log(1.0 + r0 * r0);
-                    e1 += alpha * log(1.0 + r1 * r1);
-                }
-            }
-            __syncwarp();
-        } else {
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                const double2 x = *reinterpret_cast<const double2*>(sh.Xw + (mt * 8 + ar) * kCols + 2 * q);
-                e0 += x.x * g[mt][0];
-                e1 += x.y * g[mt][1];
-            }
-            e0 *= 0.5; e1 *= 0.5;
-        }
-        e0 = col_sum(e0); e1 = col_sum(e1);
+        if (want_e) { e0 = col_sum(e0); e1 = col_sum(e1); }
     };
 
     auto kinetic2 = [&](double& k0, double& k1) {
@@ -219,167 +229,187 @@ dense_sample_kernel(const __grid_constant__ LaunchParams p) {
         __syncwarp();
     };
 
-    // hmc_state.py:86-100 on the warp's 8 particles; g must hold dEdX(Xw) on entry
-    auto leapfrog_L = [&]() {
-        for (int s = 0; s < L; ++s) {
+    for (;;) {
+        unsigned long long grp = 0;
+        if (lane == 0) grp = atomicAdd(work_head, 1ull);
+        grp = __shfl_sync(0xffffffffu, grp, 0);
+        if ((long long)(grp * kCols) >= p.n) break;
+        i0 = (long long)grp * kCols;                  // first particle of this group
+        ic = i0 + 2 * q;                              // this lane's column pair
+        colv[0] = ic < p.n; colv[1] = ic + 1 < p.n;
+        // per-particle bookkeeping lives in lanes 0..7 (lane c <-> particle i0 + c)
+        ip = i0 + lane;
+        plive = lane < kCols && ip < p.n;
+        cflags = 0; Hc = 0.0; dwell = 0.0; failed = false;
+        if (plive && sampler == MJHMC_SAMPLER_MARKOV_JUMP) { cflags = p.ca_in[ip]; Hc = ((const double*)p.Hc_in)[ip]; }
+
+        for (int it = 0; it < p.n_iter; ++it) {
+            const unsigned long long attempt = p.attempt0 + (unsigned long long)it;
+            const double* Xc = (const double*)(it == 0 ? p.Xin : p.Xout);
+            const double* Vc = (const double*)(it == 0 ? p.Vin : p.Vout);
+            double* Xo = (double*)p.Xout;
+            double* Vo = (double*)p.Vout;
+            const bool active = plive && !failed;
+
+            // ---- trajectories: pass 0 = FLF energy where the cache does not hold it
+            //      (hmc_state.py:109-119), pass 1 = current energy + the L proposal (hmc_state.py:93-100)
+            double Hflf = Hc, H = 0.0, Hl = 0.0;
+            bool need = false;
+            int first_pass = 1;
+            if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
+                need = active && !(cflags & 2u);
+                if (active && !(cflags & 1u)) n_E += 1;                 // the reference evaluates it here
+                if (__any_sync(0xffffffffu, need)) first_pass = 0;
+            }
+            for (int pass = first_pass; pass < 2; ++pass) {
+                load_state(Xc, Vc, pass == 0 ? -1.0 : 1.0);
+                double k0, k1, e0, e1;
+                for (int st = 0; st <= L; ++st) {                       // st = 0: only dEdX (and E) of the start point
+                    if (st > 0) {
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                v[mt][0] += nhe * g[mt][0];
-                v[mt][1] += nhe * g[mt][1];
-                double2* xp = reinterpret_cast<double2*>(sh.Xw + (mt * 8 + ar) * kCols + 2 * q);
-                double2 x = *xp;
-                x.x += eps * v[mt][0];
-                x.y += eps * v[mt][1];
-                *xp = x;
+                        for (int mt = 0; mt < MT; ++mt) {
+                            v[mt][0] += nhe * g[mt][0];
+                            v[mt][1] += nhe * g[mt][1];
+                            double2* xp = reinterpret_cast<double2*>(sh.Xw + (mt * 8 + ar) * kCols + 2 * q);
+                            double2 x = *xp;
+                            x.x += eps * v[mt][0];
+                            x.y += eps * v[mt][1];
+                            *xp = x;
+                        }
+                        __syncwarp();
+                    }
+                    const bool want_e = st == 0 || st == L;
+                    gradient(want_e, e0, e1);
+                    if (st > 0) {
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) { v[mt][0] += nhe * g[mt][0]; v[mt][1] += nhe * g[mt][1]; }
+                    }
+                    if (want_e) {
+                        kinetic2(k0, k1);
+                        const double h = col_pick(e0 + k0, e1 + k1, lane & 7);      // EX + EV, hmc_state.py:80-84
+                        if (st == 0) { if (pass == 1) H = h; }
+                        if (st == L) { if (pass == 0) { if (need) { Hflf = h; n_exec += 1; } } else Hl = h; }
+                    }
+                }
+            }
+            if (active) { n_E += 1; n_exec += 1; }
+
+            // ---- decision per particle (lanes 0..7)
+            unsigned int coin = 0;
+            if (sampler == MJHMC_SAMPLER_DISCRETE) {
+                if (lane == 0) coin = draw_coin(p, attempt) < p.p_r;
+                coin = __shfl_sync(0xffffffffu, coin, 0);
+            }
+            // take: 0 keep, 1 proposal, 2 proposal with flipped momentum; flip / refresh of the resulting momentum
+            unsigned int take = 0, flip = 0, refresh = 0, choice = 0;
+            if (active) {
+                if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
+                    const Decision dc = decide_mj(p, ip, attempt, H - Hl, H - Hflf);
+                    if (dc.fail) { report_failure(p, it); failed = true; }
+                    else {
+                        choice = dc.choice; dwell = dc.dwell;
+                        if (choice == 0) { take = 1; Hc = H; cflags = 3u; n_l += 1; }
+                        else if (choice == 1) { flip = 1; Hc = Hl; cflags = 2u; n_f += 1; }
+                        else { refresh = 1; cflags = 0u; n_r += 1; }
+                    }
+                } else if (sampler == MJHMC_SAMPLER_CONTINUOUS_TIME) {
+                    const Decision dc = decide_ct(p, ip, attempt, H - Hl);
+                    if (dc.fail) { report_failure(p, it); failed = true; }
+                    else {
+                        choice = dc.choice; dwell = dc.dwell;
+                        if (choice == 1) { take = 2; n_fl += 1; }
+                        else if (choice == 0) { flip = 1; n_f += 1; }
+                        else { refresh = 1; n_r += 1; }
+                    }
+                } else {
+                    const Decision dc = decide_discrete(p, ip, attempt, H - Hl, coin != 0);
+                    choice = dc.choice;
+                    const bool acc = choice & 1u, fl = choice & 2u;
+                    if (acc) take = 2;
+                    flip = fl; refresh = (choice & 4u) ? 1u : 0u;
+                    n_l += (acc && fl); n_f += (fl && !acc); n_fl += (acc && !fl); n_r += refresh;
+                }
+            }
+            const unsigned int ok = (active && !failed) ? 1u : 0u;
+            const unsigned int code = take | (flip << 2) | (refresh << 3) | (ok << 4);
+
+            // ---- apply to this lane's column pair
+    #pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const unsigned int cd = __shfl_sync(0xffffffffu, code, 2 * q + e);
+                const long long i = ic + e;
+                if (!colv[e]) continue;
+                const unsigned int tk = cd & 3u, fp = (cd >> 2) & 1u, rf = (cd >> 3) & 1u, okc = (cd >> 4) & 1u;
+    #pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int r = mt * 8 + ar;
+                    if (r >= d) continue;
+                    const long long o = (long long)r * p.ld + i;
+                    double xn, vn;
+                    if (okc && tk) {
+                        xn = sh.Xw[r * kCols + 2 * q + e];
+                        vn = tk == 1 ? v[mt][e] : -v[mt][e];
+                    } else {
+                        xn = Xc[o];
+                        vn = Vc[o];
+                    }
+                    if (okc && fp) vn = -vn;
+                    if (okc && rf) {
+                        double z0, z1;
+                        normal_pair(p, i, attempt, r >> 1, d, z0, z1);
+                        vn = vn * p.r_keep + ((r & 1) ? z1 : z0) * p.r_mix;        // hmc_state.py:126
+                    }
+                    Xo[o] = xn;
+                    Vo[o] = vn;
+                    if (okc && p.samples) ((double*)p.samples)[(long long)r * p.s_stride_k + (long long)it * p.s_stride_it + i] = xn;
+                }
+            }
+            if (active && !failed) {
+                if (p.dwell) p.dwell[(long long)it * p.n + ip] = dwell;
+                if (p.choice) p.choice[(long long)it * p.n + ip] = (uint8_t)choice;
             }
             __syncwarp();
-            gradient();
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) { v[mt][0] += nhe * g[mt][0]; v[mt][1] += nhe * g[mt][1]; }
-        }
-    };
-
-    for (int it = 0; it < p.n_iter; ++it) {
-        const unsigned long long attempt = p.attempt0 + (unsigned long long)it;
-        const double* Xc = (const double*)(it == 0 ? p.Xin : p.Xout);
-        const double* Vc = (const double*)(it == 0 ? p.Vin : p.Vout);
-        double* Xo = (double*)p.Xout;
-        double* Vo = (double*)p.Vout;
-        const bool active = plive && !failed;
-
-        // ---- FLF energy where the cache does not hold it (hmc_state.py:109-119)
-        double Hflf = Hc;
-        if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
-            const bool need = active && !(cflags & 2u);
-            if (active && !(cflags & 1u)) n_E += 1;
-            if (__any_sync(0xffffffffu, need)) {
-                load_state(Xc, Vc, -1.0);
-                gradient();
-                leapfrog_L();
-                double k0, k1, e0, e1;
-                kinetic2(k0, k1);
-                energy(e0, e1);
-                const double h = col_pick(e0 + k0, e1 + k1, lane & 7);
-                if (need) { Hflf = h; n_exec += 1; }
-            }
         }
 
-        // ---- current energy and the L proposal (hmc_state.py:93-100)
-        load_state(Xc, Vc, 1.0);
-        gradient();
-        double k0, k1, e0, e1;
-        kinetic2(k0, k1);
-        energy(e0, e1);
-        const double H = col_pick(e0 + k0, e1 + k1, lane & 7);          // EX + EV, hmc_state.py:80-84
-        leapfrog_L();
-        kinetic2(k0, k1);
-        energy(e0, e1);
-        const double Hl = col_pick(e0 + k0, e1 + k1, lane & 7);
-        if (active) { n_E += 1; n_exec += 1; }
-
-        // ---- decision per particle (lanes 0..7)
-        unsigned int coin = 0;
-        if (sampler == MJHMC_SAMPLER_DISCRETE) {
-            if (lane == 0) coin = draw_coin(p, attempt) < p.p_r;
-            coin = __shfl_sync(0xffffffffu, coin, 0);
+        if (plive) {
+            if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) { p.ca_out[ip] = (uint8_t)cflags; ((double*)p.Hc_out)[ip] = Hc; }
+            if (p.dwell_last && sampler != MJHMC_SAMPLER_DISCRETE) p.dwell_last[ip] = dwell;
         }
-        // take: 0 keep, 1 proposal, 2 proposal with flipped momentum; flip / refresh of the resulting momentum
-        unsigned int take = 0, flip = 0, refresh = 0, choice = 0;
-        if (active) {
-            if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
-                const Decision dc = decide_mj(p, ip, attempt, H - Hl, H - Hflf);
-                if (dc.fail) { report_failure(p, it); failed = true; }
-                else {
-                    choice = dc.choice; dwell = dc.dwell;
-                    if (choice == 0) { take = 1; Hc = H; cflags = 3u; n_l += 1; }
-                    else if (choice == 1) { flip = 1; Hc = Hl; cflags = 2u; n_f += 1; }
-                    else { refresh = 1; cflags = 0u; n_r += 1; }
+        if (p.n_iter == 0) {
+            // nothing ran: the state still has to reach the output buffers
+            load_state((const double*)p.Xin, (const double*)p.Vin, 1.0);
+    #pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (!colv[e]) continue;
+    #pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int r = mt * 8 + ar;
+                    if (r >= d) continue;
+                    ((double*)p.Xout)[(long long)r * p.ld + ic + e] = sh.Xw[r * kCols + 2 * q + e];
+                    ((double*)p.Vout)[(long long)r * p.ld + ic + e] = v[mt][e];
                 }
-            } else if (sampler == MJHMC_SAMPLER_CONTINUOUS_TIME) {
-                const Decision dc = decide_ct(p, ip, attempt, H - Hl);
-                if (dc.fail) { report_failure(p, it); failed = true; }
-                else {
-                    choice = dc.choice; dwell = dc.dwell;
-                    if (choice == 1) { take = 2; n_fl += 1; }
-                    else if (choice == 0) { flip = 1; n_f += 1; }
-                    else { refresh = 1; n_r += 1; }
-                }
-            } else {
-                const Decision dc = decide_discrete(p, ip, attempt, H - Hl, coin != 0);
-                choice = dc.choice;
-                const bool acc = choice & 1u, fl = choice & 2u;
-                if (acc) take = 2;
-                flip = fl; refresh = (choice & 4u) ? 1u : 0u;
-                n_l += (acc && fl); n_f += (fl && !acc); n_fl += (acc && !fl); n_r += refresh;
-            }
-        }
-        const unsigned int ok = (active && !failed) ? 1u : 0u;
-        const unsigned int code = take | (flip << 2) | (refresh << 3) | (ok << 4);
-
-        // ---- apply to this lane's column pair
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const unsigned int cd = __shfl_sync(0xffffffffu, code, 2 * q + e);
-            const long long i = ic + e;
-            if (!colv[e]) continue;
-            const unsigned int tk = cd & 3u, fp = (cd >> 2) & 1u, rf = (cd >> 3) & 1u, okc = (cd >> 4) & 1u;
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                const int r = mt * 8 + ar;
-                if (r >= d) continue;
-                const long long o = (long long)r * p.ld + i;
-                double xn, vn;
-                if (okc && tk) {
-                    xn = sh.Xw[r * kCols + 2 * q + e];
-                    vn = tk == 1 ? v[mt][e] : -v[mt][e];
-                } else {
-                    xn = Xc[o];
-                    vn = Vc[o];
-                }
-                if (okc && fp) vn = -vn;
-                if (okc && rf) {
-                    double z0, z1;
-                    normal_pair(p, i, attempt, r >> 1, d, z0, z1);
-                    vn = vn * p.r_keep + ((r & 1) ? z1 : z0) * p.r_mix;        // hmc_state.py:126
-                }
-                Xo[o] = xn;
-                Vo[o] = vn;
-                if (okc && p.samples) ((double*)p.samples)[(long long)r * p.s_stride_k + (long long)it * p.s_stride_it + i] = xn;
-            }
-        }
-        if (active && !failed) {
-            if (p.dwell) p.dwell[(long long)it * p.n + ip] = dwell;
-            if (p.choice) p.choice[(long long)it * p.n + ip] = (uint8_t)choice;
-        }
-        __syncwarp();
-    }
-
-    if (plive) {
-        if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) { p.ca_out[ip] = (uint8_t)cflags; ((double*)p.Hc_out)[ip] = Hc; }
-        if (p.dwell_last && sampler != MJHMC_SAMPLER_DISCRETE) p.dwell_last[ip] = dwell;
-    }
-    if (p.n_iter == 0) {
-        // nothing ran: the state still has to reach the output buffers
-        load_state((const double*)p.Xin, (const double*)p.Vin, 1.0);
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            if (!colv[e]) continue;
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                const int r = mt * 8 + ar;
-                if (r >= d) continue;
-                ((double*)p.Xout)[(long long)r * p.ld + ic + e] = sh.Xw[r * kCols + 2 * q + e];
-                ((double*)p.Vout)[(long long)r * p.ld + ic + e] = v[mt][e];
             }
         }
     }
+
+    // per-warp flush (no CTA barrier: warps retire independently)
     const unsigned int loc[6] = {n_l, n_f, n_fl, n_r, n_E, n_exec};
-    flush_counters(p.counters, loc, (unsigned long long)L);
+    const int slot[6] = {MJHMC_CNT_L, MJHMC_CNT_F, MJHMC_CNT_FL, MJHMC_CNT_R, MJHMC_CNT_E, MJHMC_CNT_EXEC};
+    unsigned long long* row = p.counters + (size_t)((blockIdx.x * 8 + warp) % MJHMC_COUNTER_STRIPES) * MJHMC_N_COUNTERS;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        const unsigned long long sum = __reduce_add_sync(0xffffffffu, loc[c]);
+        if (lane == 0 && sum) {
+            atomicAdd(row + slot[c], c == 5 ? sum * (unsigned long long)L : sum);
+            if (c == 4) atomicAdd(row + MJHMC_CNT_DEDX, sum * (unsigned long long)L);
+        }
+    }
 }
 
 static size_t dense_smem_bytes(int MT, int d, bool pot, int nwarps) {
-    const int rows = 8 * MT, kpad = (d + 3) & ~3, ld = dense_ld(kpad);
-    size_t doubles = (size_t)rows * ld * (pot ? 2 : 1) + (pot ? 2 * rows : 0) +
+    const int rows = 8 * MT, ld = 8 * MT + 4;
+    (void)d;
+    size_t doubles = (size_t)rows * ld + (pot ? 2 * rows : 0) +
                      (size_t)nwarps * (pot ? 2 : 1) * rows * kCols;
     return doubles * sizeof(double);
 }
@@ -413,8 +443,12 @@ static cudaError_t launch_dense_T(const LaunchParams& p, cudaStream_t stream) {
     const size_t smem = dense_smem_bytes(MT, p.d, POT, nwarps);
     cudaError_t e = cudaFuncSetAttribute(dense_sample_kernel<MT, POT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const long long per_cta = (long long)nwarps * kCols;
-    const long long blocks = (p.n + per_cta - 1) / per_cta;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long groups = (p.n + kCols - 1) / kCols;
+    long long blocks = (groups + nwarps - 1) / nwarps;
+    if (blocks > sms) blocks = sms;                            // one persistent CTA per SM
     dense_sample_kernel<MT, POT><<<(unsigned)blocks, nwarps * 32, smem, stream>>>(p);
     return cudaGetLastError();
 }

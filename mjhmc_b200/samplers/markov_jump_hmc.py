@@ -103,8 +103,8 @@ class _Engine(object):
             self.Hc = [torch.zeros(self.n, dtype=self.tdtype, device=self.device) for _ in range(2)]
             self.ca = [torch.zeros(self.n, dtype=torch.uint8, device=self.device) for _ in range(2)]
             self.cur = 0
-            tmpl = np.zeros((_lib.COUNTER_STRIPES, _lib.N_COUNTERS), dtype=np.int64)
-            tmpl[:, _lib.CNT_FAIL] = _lib.INT64_MAX
+            tmpl = np.zeros((_lib.COUNTER_ROWS, _lib.N_COUNTERS), dtype=np.int64)
+            tmpl[:_lib.COUNTER_STRIPES, _lib.CNT_FAIL] = _lib.INT64_MAX
             self.cnt_template = torch.as_tensor(tmpl, device=self.device)
             self.counters = self.cnt_template.clone()
             self.dwell_last = torch.zeros(self.n, dtype=torch.float64, device=self.device)
@@ -519,11 +519,21 @@ class HMCBase(object):
         S = self._advance(n_samples)[0]
         return self._to_host(S, preserve_order)
 
+    def _d2h(self, t):
+        """Device tensor -> fresh host numpy array through a pinned staging tensor (torch's caching
+        host allocator recycles the pinned blocks once the caller drops the array)."""
+        if self._engine.device.type != "cuda":
+            return t.numpy()
+        buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        buf.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self._engine.device).synchronize()
+        return buf.numpy()
+
     def _to_host(self, S, preserve_order):
         d, n, N = S.shape
         if preserve_order:
-            return S.permute(0, 2, 1).contiguous().cpu().numpy().astype(np.float64, copy=False)
-        return S.reshape(d, n * N).cpu().numpy().astype(np.float64, copy=False)
+            return self._d2h(S.permute(0, 2, 1).contiguous()).astype(np.float64, copy=False)
+        return self._d2h(S.reshape(d, n * N)).astype(np.float64, copy=False)
 
     def burn_in(self):
         """Runs the sample for a number of burn in sampling iterations"""
@@ -612,7 +622,7 @@ class ContinuousTimeHMC(HMCBase):
             _lib.check(eng.lib.mjhmc_resample(eng.code, d, _device.ptr(dwell_t), m, _device.ptr(r_d), m,
                                               _device.ptr(S), S.stride(0), _device.ptr(out), m, None,
                                               _device.ptr(scratch), eng._stream()), "resample")
-            return out.cpu().numpy().astype(np.float64, copy=False)
+            return self._d2h(out).astype(np.float64, copy=False)
 
 
 class MarkovJumpHMC(ContinuousTimeHMC):
