@@ -26,7 +26,7 @@ DIM_GROUPS = [(1, 2), (3, 4), (6, 8), (10, 16)]
 
 def _units():
     units = []
-    for name in ("api", "unfused", "analysis", "dense"):
+    for name in ("api", "unfused", "analysis", "dense", "dense_tc"):
         units.append((name, os.path.join(CSRC, name + ".cu"), []))
     for tname, ctype in (("f64", "double"), ("f32", "float")):
         for g, (da, db) in enumerate(DIM_GROUPS):

@@ -4,4 +4,7 @@
 namespace mjhmc {
 bool dense_supported(int dtype, int kind, int ndims, int nbasis);
 cudaError_t launch_dense(int dtype, int kind, const LaunchParams& p, cudaStream_t stream);
+// fp32 states on tcgen05 / TMEM / TMA (dense_tc.cu)
+bool dense_tf32_supported(int kind, int ndims);
+cudaError_t launch_dense_tf32(const LaunchParams& p, cudaStream_t stream);
 }
