@@ -46,6 +46,9 @@ WORKLOADS = {
     "gauss100d_mjhmc": dict(dist="GaussianRot", ndims=100, n=1_000_000, sampler="MarkovJumpHMC",
                             epsilon=1.4581446647644043, beta=0.009999999776482582, L=25, iters=2,
                             source="search/MJHMC_log_gauss/params_2.json; J = Q^T diag(10**linspace(-6,0,100)) Q"),
+    "gauss100d_mjhmc_f32": dict(dist="GaussianRot", ndims=100, n=1_000_000, sampler="MarkovJumpHMC",
+                                epsilon=1.4581446647644043, beta=0.009999999776482582, L=25, iters=2, dtype="float32",
+                                source="search/MJHMC_log_gauss/params_2.json; fp32 states, tcgen05 3xTF32"),
     "pot100d_mjhmc": dict(dist="ProductOfT", ndims=100, n=1_000_000, sampler="MarkovJumpHMC",
                           epsilon=0.4827975928783417, beta=0.10154356807470322, L=10, iters=2,
                           source="search/MJHMC_poe_100/params.json; dense W = randn/sqrt(100)"),
@@ -222,7 +225,8 @@ class ClockSampler(object):
         return out
 
 
-def make_sampler(w, rank, dtype=DTYPE, seed=2024):
+def make_sampler(w, rank, dtype=None, seed=2024):
+    dtype = dtype or w.get("dtype", DTYPE)
     from mjhmc_b200.misc import distributions as D
     from mjhmc_b200.samplers import markov_jump_hmc as S
     n, d = w["n"], w["ndims"]
@@ -331,7 +335,7 @@ def run_b200(args, w):
         dist_pkg.all_reduce(ee, op=dist_pkg.ReduceOp.MAX)
         dist_pkg.all_reduce(ge, op=dist_pkg.ReduceOp.SUM)
     e2e_value = int(ge.item()) / float(ee.item())
-    S = 8
+    S = 4 if w.get("dtype") == "float32" else 8
     h2d = 2 * w["ndims"] * w["n"] * S + w["n"] * (S + 1)
     d2h = res.nbytes
 
@@ -344,10 +348,16 @@ def run_b200(args, w):
             # dense-contraction energies: algorithmic flops per leapfrog step = 2 d^2 (S x) resp. 4 d nb (W^T x, W G)
             fl = (2 if w["dist"] == "GaussianRot" else 4) * w["ndims"] ** 2
             tf = grads_all * fl / (ms_max * 1e-3) / 1e12 / world
-            roofline = {"bound": "tensor", "achieved": tf, "peak": 40.0, "unit": "TFLOP/s", "frac": tf / 40.0,
-                        "traffic": None, "kernel": "dense_sample_kernel (mma.sync m8n8k4 f64 = DMMA)",
-                        "peak_source": "nominal B200 fp64 tensor-core rate; MEASURED_PEAKS.json has no fp64 figure "
-                                       "(its bf16 cuBLAS number does not apply to an fp64 path)",
+            f32 = w.get("dtype") == "float32"
+            tpeak = 1100.0 / 3.0 if f32 else 40.0
+            roofline = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                        "traffic": None,
+                        "kernel": "dense_tf32_kernel (tcgen05.mma kind::tf32, 3 MMAs per product)" if f32
+                                  else "dense_sample_kernel (mma.sync m8n8k4 f64 = DMMA)",
+                        "peak_source": ("nominal B200 dense tf32 rate 1.1 PFLOP/s divided by the 3 MMAs of the 3xTF32 split"
+                                        if f32 else
+                                        "nominal B200 fp64 tensor-core rate; MEASURED_PEAKS.json has no fp64 figure "
+                                        "(its bf16 cuBLAS number does not apply to an fp64 path)"),
                         "algorithmic_flops_per_leapfrog_step": fl, "launch_ms": launch_ms,
                         "hbm_gbs": achieved, "note": "ncu sm__pipe_tensor_cycles_active in profiles/r1_dense_*.txt"}
         else:
@@ -360,7 +370,7 @@ def run_b200(args, w):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if w.get("dtype") == "float32" else "f64", "data": "synthetic",
             "config": {"workload": "%s: %s %d-d, %d particles per GPU, %s eps=%g beta=%g L=%d (%s); %d sampling "
                                    "iterations per step in one fused launch" % (
                                        args.workload, w["dist"], w["ndims"], w["n"], w["sampler"], w["epsilon"], w["beta"],

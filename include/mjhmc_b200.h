@@ -40,7 +40,8 @@ enum {
     MJHMC_DIST_ROUGH_WELL     = 2, /* distributions.py:295-304  p[0]=scale1 p[1]=scale2              */
     MJHMC_DIST_FUNNEL         = 3, /* tf_distributions.py:143-147 (Neal's funnel)  p[0]=scale        */
     MJHMC_DIST_FUNNEL_LITERAL = 4, /* tf_distributions.py:158-165 as written        p[0]=scale        */
-    MJHMC_DIST_DENSE_GAUSSIAN = 5, /* distributions.py:268-273 full J; a0 = (J+J^T)/2 [ndims x ndims] */
+    MJHMC_DIST_DENSE_GAUSSIAN = 5, /* distributions.py:268-273 full J; a0 = (J+J^T)/2 [ndims x ndims];
+                                      fp32 only: a1 = workspace filled by mjhmc_dense_tf32_prepare */
     MJHMC_DIST_PRODUCT_OF_T   = 6  /* distributions.py:420-433; a0=W [ndims x nbasis], a1=nu, a2=b    */
 };
 
@@ -179,6 +180,12 @@ int mjhmc_transition(int32_t dtype, int32_t ndims, const mjhmc_hp *hp, const mjh
                      int64_t n, int64_t ld, const mjhmc_full_state *cur, const mjhmc_full_state *prop,
                      const void *H_flf, void *H_cache, uint8_t *cache_active,
                      const mjhmc_outputs *o, void *stream);
+
+/* fp32 full-covariance Gaussian on the tcgen05 tensor cores: the kernel consumes the matrix pre-tiled into
+ * K-major 8x16-byte core matrices and split into tf32 hi / lo parts.  The caller allocates
+ * mjhmc_dense_tf32_workspace_bytes(ndims) bytes, points dist->a1 at them and calls prepare once. */
+int64_t mjhmc_dense_tf32_workspace_bytes(int32_t ndims);
+int mjhmc_dense_tf32_prepare(const mjhmc_dist *dist, void *stream);
 
 /* Folds the striped counter rows into host int64[MJHMC_N_COUNTERS] (synchronises the stream). */
 int mjhmc_counters_read(const int64_t *counters, int64_t *out_host, void *stream);

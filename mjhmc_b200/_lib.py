@@ -71,6 +71,8 @@ SYMBOLS = {
                              C.c_void_p]),
     "mjhmc_transition": (C.c_int, [C.c_int32, C.c_int32, _P(HP), _P(RNG), C.c_int64, C.c_int64, _P(FullState),
                                    _P(FullState), C.c_void_p, C.c_void_p, C.c_void_p, _P(Outputs), C.c_void_p]),
+    "mjhmc_dense_tf32_workspace_bytes": (C.c_int64, [C.c_int32]),
+    "mjhmc_dense_tf32_prepare": (C.c_int, [_P(Dist), C.c_void_p]),
     "mjhmc_counters_read": (C.c_int, [C.c_void_p, _P(C.c_int64), C.c_void_p]),
     "mjhmc_counters_reset": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mjhmc_resample_scratch_bytes": (C.c_int64, [C.c_int64]),

@@ -257,6 +257,15 @@ int mjhmc_counters_read(const int64_t* counters, int64_t* out_host, void* stream
     return 0;
 }
 
+int64_t mjhmc_dense_tf32_workspace_bytes(int32_t ndims) { return ndims > 0 ? dense_tf32_workspace_bytes(ndims) : -1; }
+
+int mjhmc_dense_tf32_prepare(const mjhmc_dist* dist, void* stream) {
+    if (check_dist(dist)) return -1;
+    if (dist->kind != MJHMC_DIST_DENSE_GAUSSIAN || dist->dtype != MJHMC_F32) return fail("tf32 workspace is for the fp32 dense Gaussian");
+    if (!dist->a1) return fail("dist->a1 (workspace) is NULL");
+    return check(dense_tf32_prepare((const float*)dist->a0, dist->ndims, (float*)dist->a1, (cudaStream_t)stream), "tf32_prep_kernel");
+}
+
 int64_t mjhmc_resample_scratch_bytes(int64_t m) { return m < 0 ? -1 : resample_scratch_bytes(m); }
 
 int mjhmc_resample(int32_t dtype, int32_t ndims, const double* dwell, int64_t m, const double* r, int64_t m_out,

@@ -7,4 +7,6 @@ cudaError_t launch_dense(int dtype, int kind, const LaunchParams& p, cudaStream_
 // fp32 states on tcgen05 / TMEM / TMA (dense_tc.cu)
 bool dense_tf32_supported(int kind, int ndims);
 cudaError_t launch_dense_tf32(const LaunchParams& p, cudaStream_t stream);
+long long dense_tf32_workspace_bytes(int ndims);
+cudaError_t dense_tf32_prepare(const float* S, int ndims, float* workspace, cudaStream_t stream);
 }

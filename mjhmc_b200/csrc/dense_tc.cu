@@ -395,27 +395,43 @@ bool dense_tf32_supported(int kind, int ndims) {
     return kind == MJHMC_DIST_DENSE_GAUSSIAN && ndims >= 1 && ndims <= kTcMaxDim;
 }
 
+static void tf32_shape(int d, int& ksteps, int& N, int& kcores, int& ngroups) {
+    ksteps = (d + 7) >> 3; N = ((d + 15) >> 4) << 4; kcores = ksteps * 2; ngroups = N >> 3;
+}
+
+long long dense_tf32_workspace_bytes(int ndims) {
+    int ksteps, N, kcores, ngroups;
+    tf32_shape(ndims, ksteps, N, kcores, ngroups);
+    return 2ll * ngroups * kcores * 128;
+}
+
+// Fills the pre-tiled hi / lo copy of S (once per distribution; the sampler launches only read it).
+cudaError_t dense_tf32_prepare(const float* S, int ndims, float* workspace, cudaStream_t stream) {
+    int ksteps, N, kcores, ngroups;
+    tf32_shape(ndims, ksteps, N, kcores, ngroups);
+    tf32_prep_kernel<<<32, 256, 0, stream>>>(S, ndims, ngroups, kcores, workspace);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_dense_tf32(const LaunchParams& p, cudaStream_t stream) {
-    const int ksteps = (p.d + 7) >> 3, N = ((p.d + 15) >> 4) << 4, kcores = ksteps * 2, ngroups = N >> 3;
+    int ksteps, N, kcores, ngroups;
+    tf32_shape(p.d, ksteps, N, kcores, ngroups);
+    if (!p.a1) return cudaErrorInvalidValue;                   // the pre-tiled matrix (mjhmc_dense_tf32_prepare)
     const size_t a_bytes = (size_t)kcores * kTcCoreColBytes;
     const size_t b_bytes = (size_t)ngroups * kcores * 128;
     const size_t smem = 2 * a_bytes + 2 * b_bytes + 1024;
-    float* Btiled = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&Btiled, 2 * b_bytes, stream);
-    if (e != cudaSuccess) return e;
-    tf32_prep_kernel<<<32, 256, 0, stream>>>((const float*)p.a0, p.d, ngroups, kcores, Btiled);
-    e = cudaFuncSetAttribute(dense_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) {
-        int dev = 0, sms = 148;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        long long tiles = (p.n + kTcThreads - 1) / kTcThreads;
-        if (tiles > sms) tiles = sms;
-        dense_tf32_kernel<<<(unsigned)tiles, kTcThreads, smem, stream>>>(p, Btiled);
-        e = cudaGetLastError();
     }
-    cudaFreeAsync(Btiled, stream);
-    return e;
+    cudaError_t e = cudaFuncSetAttribute(dense_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    long long tiles = (p.n + kTcThreads - 1) / kTcThreads;
+    if (tiles > sms) tiles = sms;
+    dense_tf32_kernel<<<(unsigned)tiles, kTcThreads, smem, stream>>>(p, (const float*)p.a1);
+    return cudaGetLastError();
 }
 
 }  // namespace mjhmc

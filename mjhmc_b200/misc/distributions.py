@@ -209,6 +209,13 @@ class Gaussian(_DeviceEnergy):
             j = _device.to_device(np.diag(self.J), dtype, device)
             return self._desc(_lib.DIST_DIAG_GAUSSIAN, dtype, arrays=(j,))
         S = _device.to_device((self.J + self.J.T) / 2., dtype, device)      # dEdX = J X/2 + J^T X/2
+        if _device.norm_dtype(dtype) == "float32" and device is not None:
+            # tcgen05 path: the matrix pre-tiled and split into tf32 hi / lo parts, prepared once
+            lib = _lib.load()
+            ws = torch.empty(int(lib.mjhmc_dense_tf32_workspace_bytes(self.ndims)), dtype=torch.uint8, device=device)
+            desc, keep = self._desc(_lib.DIST_DENSE_GAUSSIAN, dtype, arrays=(S, ws))
+            _lib.check(lib.mjhmc_dense_tf32_prepare(desc, _device.stream_ptr(device)), "dense_tf32_prepare")
+            return desc, keep
         return self._desc(_lib.DIST_DENSE_GAUSSIAN, dtype, arrays=(S,))
 
 
