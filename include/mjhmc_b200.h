@@ -202,12 +202,18 @@ int mjhmc_resample(int32_t dtype, int32_t ndims, const double *dwell, int64_t m,
                    const double *r, int64_t m_out, const void *samples, int64_t ld_in,
                    void *out, int64_t ld_out, int64_t *idx_out, void *scratch, void *stream);
 
-/* Replaces autocor.fft_autocor (misc/autocor.py:37-49) as a direct circular product:
- * ac[tau] = sum_{k,i,t} x[k,i,t] * x[k,i,(t+tau) mod T], NOT normalised (the caller divides by
- * ac[0] after the cross-GPU all-reduce).  samples element (k, t, i) at k*stride_k + t*stride_it + i.
- * ac: (n_lags,) double, +=. */
+/* Replaces autocor.fft_autocor (misc/autocor.py:37-49, circular = 1) and slow_autocorrelation (:177-211,
+ * circular = 0) as direct products:
+ *   circular: ac[tau] += sum_{k,i,t}        x[k,i,t] * x[k,i,(t+tau) mod T]
+ *   linear  : ac[tau] += sum_{k,i,t<T-tau}  x[k,i,t] * x[k,i,t+tau]
+ * NOT normalised (the caller divides after the cross-GPU all-reduce).
+ * samples element (k, t, i) at k*stride_k + t*stride_it + i.  ac: (n_lags,) double. */
 int mjhmc_autocorr(int32_t dtype, int32_t ndims, const void *samples, int64_t stride_k, int64_t stride_it,
-                   int64_t n, int32_t T, int32_t n_lags, double *ac, void *stream);
+                   int64_t n, int32_t T, int32_t n_lags, int32_t circular, double *ac, void *stream);
+
+/* Replaces the Welford loop of online_variance (misc/gen_mj_init.py:76-98) for one chunk of samples:
+ * out[0] += sum x, out[1] += sum x^2 over `count` contiguous elements (double accumulation). */
+int mjhmc_moments(int32_t dtype, const void *x, int64_t count, double *out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ __version__ = "0.1.0"
 
 def install_alias(name="mjhmc"):
     from . import misc, samplers
-    from .misc import distributions, utils
+    from .misc import autocor, distributions, gen_mj_init, utils
     from .samplers import hmc_state, markov_jump_hmc
     pkg = sys.modules[__name__]
     sys.modules[name] = pkg
@@ -20,6 +20,8 @@ def install_alias(name="mjhmc"):
     sys.modules[name + ".misc.distributions"] = distributions
     sys.modules[name + ".misc.tf_distributions"] = distributions      # Funnel's reference location
     sys.modules[name + ".misc.utils"] = utils
+    sys.modules[name + ".misc.autocor"] = autocor
+    sys.modules[name + ".misc.gen_mj_init"] = gen_mj_init
     sys.modules[name + ".samplers"] = samplers
     sys.modules[name + ".samplers.markov_jump_hmc"] = markov_jump_hmc
     sys.modules[name + ".samplers.hmc_state"] = hmc_state

@@ -79,7 +79,8 @@ SYMBOLS = {
     "mjhmc_resample": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                  C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mjhmc_autocorr": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
-                                 C.c_int32, C.c_void_p, C.c_void_p]),
+                                 C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mjhmc_moments": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -141,7 +141,7 @@ constexpr int kAcG = 16;
 template <typename T>
 __global__ void __launch_bounds__(kAcP * kAcG) autocorr_kernel(const T* __restrict__ samples, long long stride_k,
                                                                long long stride_it, long long n, int Tn, int n_lags,
-                                                               double* __restrict__ ac) {
+                                                               int circular, double* __restrict__ ac) {
     extern __shared__ double tile[];              // [Tn][kAcP]
     __shared__ double red[kAcG][kAcP + 1];
     const int p = threadIdx.x % kAcP, g = threadIdx.x / kAcP;
@@ -156,10 +156,15 @@ __global__ void __launch_bounds__(kAcP * kAcG) autocorr_kernel(const T* __restri
         const int tau = tau0 + g;
         double acc = 0.0;
         if (tau < n_lags) {
-            int t2 = tau % Tn;
-            for (int t = 0; t < Tn; ++t) {
-                acc += tile[t * kAcP + p] * tile[t2 * kAcP + p];
-                t2 = t2 + 1 == Tn ? 0 : t2 + 1;
+            if (circular) {
+                int t2 = tau % Tn;
+                for (int t = 0; t < Tn; ++t) {
+                    acc += tile[t * kAcP + p] * tile[t2 * kAcP + p];
+                    t2 = t2 + 1 == Tn ? 0 : t2 + 1;
+                }
+            } else {
+                // linear window: sum_{t < T - tau} x[t] x[t + tau]  (slow_autocorrelation, autocor.py:177-211)
+                for (int t = 0; t + tau < Tn; ++t) acc += tile[t * kAcP + p] * tile[(t + tau) * kAcP + p];
             }
         }
         red[g][p] = acc;
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(kAcP * kAcG) autocorr_kernel(const T* __restri
 }
 
 cudaError_t launch_autocorr(int dtype, int d, const void* samples, long long stride_k, long long stride_it,
-                            long long n, int Tn, int n_lags, double* ac, cudaStream_t s) {
+                            long long n, int Tn, int n_lags, int circular, double* ac, cudaStream_t s) {
     if (n == 0 || Tn == 0 || n_lags == 0) return cudaSuccess;
     const size_t smem = sizeof(double) * (size_t)Tn * kAcP;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
@@ -184,12 +189,46 @@ cudaError_t launch_autocorr(int dtype, int d, const void* samples, long long str
     if (dtype == MJHMC_F64) {
         e = cudaFuncSetAttribute(autocorr_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        autocorr_kernel<double><<<grid, kAcP * kAcG, smem, s>>>((const double*)samples, stride_k, stride_it, n, Tn, n_lags, ac);
+        autocorr_kernel<double><<<grid, kAcP * kAcG, smem, s>>>((const double*)samples, stride_k, stride_it, n, Tn, n_lags, circular, ac);
     } else {
         e = cudaFuncSetAttribute(autocorr_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        autocorr_kernel<float><<<grid, kAcP * kAcG, smem, s>>>((const float*)samples, stride_k, stride_it, n, Tn, n_lags, ac);
+        autocorr_kernel<float><<<grid, kAcP * kAcG, smem, s>>>((const float*)samples, stride_k, stride_it, n, Tn, n_lags, circular, ac);
     }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ moments
+// out[0] += sum x, out[1] += sum x^2 over `count` contiguous elements (online_variance of
+// misc/gen_mj_init.py:76-98 in chunks: the caller merges the chunks with Chan's formula).
+template <typename T>
+__global__ void __launch_bounds__(256) moments_kernel(const T* __restrict__ x, long long count, double* __restrict__ out) {
+    __shared__ double sm[2][8];
+    double s = 0.0, s2 = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        const double v = (double)x[i];
+        s += v;
+        s2 += v * v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sm[0][warp] = s; sm[1][warp] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 8; ++w) { a += sm[0][w]; b += sm[1][w]; }
+        atomicAdd(out, a);
+        atomicAdd(out + 1, b);
+    }
+}
+
+cudaError_t launch_moments(int dtype, const void* x, long long count, double* out, cudaStream_t s) {
+    if (count == 0) return cudaSuccess;
+    long long blocks = (count + 256 * 8 - 1) / (256 * 8);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (dtype == MJHMC_F64) moments_kernel<double><<<(unsigned)blocks, 256, 0, s>>>((const double*)x, count, out);
+    else moments_kernel<float><<<(unsigned)blocks, 256, 0, s>>>((const float*)x, count, out);
     return cudaGetLastError();
 }
 

@@ -279,11 +279,19 @@ int mjhmc_resample(int32_t dtype, int32_t ndims, const double* dwell, int64_t m,
 }
 
 int mjhmc_autocorr(int32_t dtype, int32_t ndims, const void* samples, int64_t stride_k, int64_t stride_it, int64_t n,
-                   int32_t T, int32_t n_lags, double* ac, void* stream) {
+                   int32_t T, int32_t n_lags, int32_t circular, double* ac, void* stream) {
     if (dtype != MJHMC_F32 && dtype != MJHMC_F64) return fail("bad dtype");
     if (n < 0 || T < 0 || n_lags < 0 || ndims <= 0) return fail("bad sizes");
     if (n && T && n_lags && (!samples || !ac)) return fail("NULL argument");
-    return check(launch_autocorr(dtype, ndims, samples, stride_k, stride_it, n, T, n_lags, ac, (cudaStream_t)stream), "autocorr");
+    return check(launch_autocorr(dtype, ndims, samples, stride_k, stride_it, n, T, n_lags, circular, ac,
+                                 (cudaStream_t)stream), "autocorr");
+}
+
+int mjhmc_moments(int32_t dtype, const void* x, int64_t count, double* out, void* stream) {
+    if (dtype != MJHMC_F32 && dtype != MJHMC_F64) return fail("bad dtype");
+    if (count < 0) return fail("bad count");
+    if (count && (!x || !out)) return fail("NULL argument");
+    return check(launch_moments(dtype, x, count, out, (cudaStream_t)stream), "moments");
 }
 
 }  // extern "C"

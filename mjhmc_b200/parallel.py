@@ -81,15 +81,16 @@ def allgather_samples(S, group=None):
     return torch.cat([p[:, :, :n] for p, n in zip(parts, sizes)], dim=2)
 
 
-def autocorr_partial(S, n_lags=None):
-    """Un-normalised circular autocorrelation sums of the LOCAL particles on the GPU (K7):
-    ac[tau] = sum_{k,i,t} x[k,t,i] x[k,(t+tau) mod T,i];  S is the device tensor (ndims, T, n_local)."""
+def autocorr_partial(S, n_lags=None, circular=True):
+    """Un-normalised autocorrelation sums of the LOCAL particles on the GPU (K7):
+    ac[tau] = sum_{k,i,t} x[k,t,i] x[k,(t+tau) mod T,i]  (circular; linear: only t + tau < T);
+    S is the device tensor (ndims, T, n_local)."""
     lib = _lib.load()
     d, T, n = S.shape
     n_lags = T if n_lags is None else int(n_lags)
     ac = torch.zeros(n_lags, dtype=torch.float64, device=S.device)
     _lib.check(lib.mjhmc_autocorr(_device.dtype_code(S.dtype), d, _device.ptr(S), S.stride(0), S.stride(1), n, T,
-                                  n_lags, _device.ptr(ac), _device.stream_ptr(S.device)), "autocorr")
+                                  n_lags, 1 if circular else 0, _device.ptr(ac), _device.stream_ptr(S.device)), "autocorr")
     return ac
 
 

@@ -490,6 +490,24 @@ class HMCBase(object):
             self._run(n, samples, 0, dwell, choice)
         return samples, dwell, choice
 
+    def _snapshot(self):
+        """Device state + counters, so a chunk of iterations can be replayed (generate_samples)."""
+        eng, d = self._engine, self.distribution
+        c = eng.cur
+        tensors = [t.clone() for t in (eng.X[c], eng.V[c], eng.Hc[c], eng.ca[c], eng.dwell_last)]
+        ints = (self._attempt, self.l_count, self.f_count, self.fl_count, self.r_count, d.E_count, d.dEdX_count,
+                self.grad_evals_executed)
+        return tensors, ints
+
+    def _restore(self, snap):
+        eng, d = self._engine, self.distribution
+        c = eng.cur
+        for dst, src in zip((eng.X[c], eng.V[c], eng.Hc[c], eng.ca[c], eng.dwell_last), snap[0]):
+            dst.copy_(src)
+        (self._attempt, self.l_count, self.f_count, self.fl_count, self.r_count, d.E_count, d.dEdX_count,
+         self.grad_evals_executed) = snap[1]
+        self._host_state = None
+
     def sampling_iteration(self):
         """Perform a single sampling step"""
         self._advance(1, record=False)
