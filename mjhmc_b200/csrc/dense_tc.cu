@@ -85,6 +85,19 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
     for (int j = 0; j < 8; ++j) r[j] = __uint_as_float(u[j]);
 }
 
+// 64 consecutive accumulator columns of this thread's TMEM lane: two x32 loads in flight, ONE wait
+// (the epilogue of a 128-thread CTA has one warp per scheduler, so every exposed TMEM round trip counts)
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&r)[64]) {
+    uint32_t u[64];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%64];\n"
+                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%65];\n"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31]), "=r"(u[32]), "=r"(u[33]), "=r"(u[34]), "=r"(u[35]), "=r"(u[36]), "=r"(u[37]), "=r"(u[38]), "=r"(u[39]), "=r"(u[40]), "=r"(u[41]), "=r"(u[42]), "=r"(u[43]), "=r"(u[44]), "=r"(u[45]), "=r"(u[46]), "=r"(u[47]), "=r"(u[48]), "=r"(u[49]), "=r"(u[50]), "=r"(u[51]), "=r"(u[52]), "=r"(u[53]), "=r"(u[54]), "=r"(u[55]), "=r"(u[56]), "=r"(u[57]), "=r"(u[58]), "=r"(u[59]), "=r"(u[60]), "=r"(u[61]), "=r"(u[62]), "=r"(u[63])
+                 : "r"(taddr), "r"(taddr + 32u) : "memory");
+#pragma unroll
+    for (int j = 0; j < 64; ++j) r[j] = __uint_as_float(u[j]);
+}
+
 // shared-memory matrix descriptors (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
     uint64_t d = 0;
@@ -261,35 +274,38 @@ dense_tf32_kernel(const __grid_constant__ LaunchParams p, const float* __restric
 
                 for (int st = 0; st <= L; ++st) {
                     tile_gradient();
-                    // ---- one sweep over my particle's gradient (TMEM -> registers, 8 dims at a time)
+                    // ---- one sweep over my particle's gradient (TMEM -> registers, 64 dims per round trip)
 #pragma unroll
-                    for (int c = 0; c < kTcMaxDim / 8; ++c) {
-                        if (c < ksteps) {
-                            float g[8];
-                            tmem_ld8(my_tmem + (uint32_t)(c * 8), g);
+                    for (int grp = 0; grp < (kTcMaxDim + 63) / 64; ++grp) {
+                        if (grp * 64 < KP) {
+                            float g[64];
+                            tmem_ld64(my_tmem + (uint32_t)(grp * 64), g);
 #pragma unroll
-                            for (int h = 0; h < 2; ++h) {              // the two 4-dim core columns of this chunk
-                                const uint32_t off = a_row_offset(tid, c * 2 + h);
-                                float4* ph = reinterpret_cast<float4*>(Ahi + off);
-                                float4* pl = reinterpret_cast<float4*>(Alo + off);
-                                const float4 xh = *ph, xl = *pl;
-                                float xs[4] = {xh.x + xl.x, xh.y + xl.y, xh.z + xl.z, xh.w + xl.w};
+                            for (int h = 0; h < 16; ++h) {             // 4-dim core columns of this group
+                                const int kc = grp * 16 + h;
+                                if (kc * 4 < kTcMaxDim && kc < kcores) {
+                                    const uint32_t off = a_row_offset(tid, kc);
+                                    float4* ph = reinterpret_cast<float4*>(Ahi + off);
+                                    float4* pl = reinterpret_cast<float4*>(Alo + off);
+                                    const float4 xh = *ph, xl = *pl;
+                                    float xs[4] = {xh.x + xl.x, xh.y + xl.y, xh.z + xl.z, xh.w + xl.w};
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const int k = c * 8 + h * 4 + j;
-                                    const float gk = g[h * 4 + j];
-                                    if (st == 0) e_start += xs[j] * gk;
-                                    if (st == L) e_end += xs[j] * gk;
-                                    if (st > 0) v[k] += nhe * gk;      // second half kick of step st
-                                    if (st < L) {                      // first half kick + drift of step st+1
-                                        v[k] += nhe * gk;
-                                        xs[j] += eps * v[k];
+                                    for (int j = 0; j < 4; ++j) {
+                                        const int k = kc * 4 + j;
+                                        const float gk = g[h * 4 + j];
+                                        if (st == 0) e_start += xs[j] * gk;
+                                        if (st == L) e_end += xs[j] * gk;
+                                        if (st > 0) v[k] += nhe * gk;  // second half kick of step st
+                                        if (st < L) {                  // first half kick + drift of step st+1
+                                            v[k] += nhe * gk;
+                                            xs[j] += eps * v[k];
+                                        }
                                     }
-                                }
-                                if (st < L) {
-                                    const float4 hi = make_float4(tf32_hi(xs[0]), tf32_hi(xs[1]), tf32_hi(xs[2]), tf32_hi(xs[3]));
-                                    *ph = hi;
-                                    *pl = make_float4(xs[0] - hi.x, xs[1] - hi.y, xs[2] - hi.z, xs[3] - hi.w);
+                                    if (st < L) {
+                                        const float4 hi = make_float4(tf32_hi(xs[0]), tf32_hi(xs[1]), tf32_hi(xs[2]), tf32_hi(xs[3]));
+                                        *ph = hi;
+                                        *pl = make_float4(xs[0] - hi.x, xs[1] - hi.y, xs[2] - hi.z, xs[3] - hi.w);
+                                    }
                                 }
                             }
                         }
