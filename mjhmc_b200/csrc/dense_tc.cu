@@ -4,9 +4,11 @@
 //
 //   dEdX = S x,  E = x.(S x)/2,  S = (J + J^T)/2          misc/distributions.py:268-273
 //
-// Mapping.  A CTA of 128 threads works on a tile of 128 particles; THREAD t OWNS PARTICLE t of the
-// tile (as in the register-resident kernel): its momentum lives in registers, its position in the
-// A-operand tile in shared memory.  The gradient of the whole tile is one accumulator
+// Mapping.  A CTA works on a tile of 128 particles with 4 threads per particle (512 threads): thread
+// (m, q) owns a quarter of the dims of particle m -- that slice of the momentum lives in its
+// registers, the position in the A-operand tile in shared memory.  (One thread per particle, the
+// first version, left one warp per scheduler and 90 % issue stalls: profiles/r1_dense_tc_v1.txt.)
+// The gradient of the whole tile is one accumulator
 //       D[128 particles x N dims] = Xtile[128 x K] . S^T[K x N]
 //   A = Xtile : K-major, no swizzle: 8-particle x 4-dim core matrices (16 bytes per particle row), the
 //       16 particle groups of one 4-dim core column contiguous (SBO = 128 B, LBO = 2 KB), so the 32
@@ -22,8 +24,13 @@
 
 namespace mjhmc {
 
-constexpr int kTcThreads = 128;
+constexpr int kTcTile = 128;                   // particles per tile (M of the MMA)
+constexpr int kTcSplit = 4;                    // threads per particle: each owns a quarter of the dims
+constexpr int kTcThreads = kTcTile * kTcSplit; // 16 warps: warp w reads TMEM lanes 32 (w % 4) ..
 constexpr int kTcMaxDim = 104;                 // padded dims (N and K of the MMA)
+constexpr int kTcMaxCores = kTcMaxDim / 4;     // 4-dim core columns of the A tile
+constexpr int kTcCoresPerThread = (kTcMaxCores + kTcSplit - 1) / kTcSplit;   // 7
+constexpr int kTcDimsPerThread = kTcCoresPerThread * 4;                      // 28
 constexpr int kTcTmemCols = 128;
 constexpr int kTcCoreColBytes = 2048;          // one 4-dim core column of the A tile: 16 particle groups x 128 B
 
@@ -85,17 +92,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
     for (int j = 0; j < 8; ++j) r[j] = __uint_as_float(u[j]);
 }
 
-// 64 consecutive accumulator columns of this thread's TMEM lane: two x32 loads in flight, ONE wait
-// (the epilogue of a 128-thread CTA has one warp per scheduler, so every exposed TMEM round trip counts)
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&r)[64]) {
-    uint32_t u[64];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%64];\n"
-                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%65];\n"
+// 32 consecutive accumulator columns of this thread's TMEM lane (load + wait in one statement)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&r)[32]) {
+    uint32_t u[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
                  "tcgen05.wait::ld.sync.aligned;"
-                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31]), "=r"(u[32]), "=r"(u[33]), "=r"(u[34]), "=r"(u[35]), "=r"(u[36]), "=r"(u[37]), "=r"(u[38]), "=r"(u[39]), "=r"(u[40]), "=r"(u[41]), "=r"(u[42]), "=r"(u[43]), "=r"(u[44]), "=r"(u[45]), "=r"(u[46]), "=r"(u[47]), "=r"(u[48]), "=r"(u[49]), "=r"(u[50]), "=r"(u[51]), "=r"(u[52]), "=r"(u[53]), "=r"(u[54]), "=r"(u[55]), "=r"(u[56]), "=r"(u[57]), "=r"(u[58]), "=r"(u[59]), "=r"(u[60]), "=r"(u[61]), "=r"(u[62]), "=r"(u[63])
-                 : "r"(taddr), "r"(taddr + 32u) : "memory");
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+                 : "r"(taddr) : "memory");
 #pragma unroll
-    for (int j = 0; j < 64; ++j) r[j] = __uint_as_float(u[j]);
+    for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(u[j]);
 }
 
 // shared-memory matrix descriptors (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
@@ -140,11 +145,12 @@ dense_tf32_kernel(const __grid_constant__ LaunchParams p, const float* __restric
     __shared__ uint32_t s_tmem;
     __shared__ unsigned long long s_tile;
     __shared__ int s_coin;
+    __shared__ float s_red[4][kTcSplit][kTcTile];     // partial e_start, e_end, ev_start, ev_end per (part, particle)
+    __shared__ unsigned int s_code[kTcTile];          // decision of each particle, broadcast to its 4 threads
 
     const int d = p.d;
     const int ksteps = (d + 7) >> 3;               // MMA K = 8
     const int N = ((d + 15) >> 4) << 4;            // MMA N: a multiple of 16 for M = 128
-    const int KP = ksteps * 8;                     // padded K (rows of the A tiles)
     const int kcores = ksteps * 2;
     const int ngroups = N >> 3;
     const uint32_t a_bytes = (uint32_t)kcores * kTcCoreColBytes;
@@ -154,6 +160,12 @@ dense_tf32_kernel(const __grid_constant__ LaunchParams p, const float* __restric
     uint8_t* Bhi = Alo + a_bytes;
     uint8_t* Blo = Bhi + b_bytes;
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int m = tid & (kTcTile - 1);             // particle of the tile
+    const int q = tid / kTcTile;                   // which slice of the dims
+    const int per = (kcores + kTcSplit - 1) / kTcSplit;
+    const int kc0 = q * per;                       // my core columns [kc0, kc1)
+    const int kc1 = min(kcores, kc0 + per);
+    const bool lead = q == 0;                      // the thread that decides for the particle
 
     // ---- one-time setup: barriers, TMEM, the matrix via TMA
     if (tid == 0) {
@@ -185,11 +197,12 @@ dense_tf32_kernel(const __grid_constant__ LaunchParams p, const float* __restric
     const int L = p.L, sampler = p.sampler;
     unsigned int n_l = 0, n_f = 0, n_fl = 0, n_r = 0, n_E = 0, n_exec = 0;
     unsigned long long* work_head = p.counters + (size_t)MJHMC_COUNTER_STRIPES * MJHMC_N_COUNTERS + 1;
-    const uint32_t my_tmem = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // my TMEM window: lane quarter of my warp, columns of my dims (a x32 load may run past them: unused)
+    const uint32_t my_tmem = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kc0 * 4);
 
-    float v[kTcMaxDim];
+    float v[kTcDimsPerThread];
 
-    // D = Xtile . S^T for the positions currently in the A tiles (all 128 threads call this)
+    // D = Xtile . S^T for the positions currently in the A tiles (all threads call this)
     auto tile_gradient = [&]() {
         fence_async_smem();                        // our generic-proxy stores to A -> visible to the tensor core
         tc_fence_before();
@@ -217,15 +230,15 @@ dense_tf32_kernel(const __grid_constant__ LaunchParams p, const float* __restric
         __syncthreads();
         const unsigned long long tile = s_tile;
         __syncthreads();
-        if ((long long)(tile * kTcThreads) >= p.n) break;
-        const long long i = (long long)tile * kTcThreads + tid;
+        if ((long long)(tile * kTcTile) >= p.n) break;
+        const long long i = (long long)tile * kTcTile + m;
         const bool live = i < p.n;
 
         unsigned int cflags = 0;
         float Hc = 0.0f;
         double dwell = 0.0;
         bool failed = false;
-        if (live && sampler == MJHMC_SAMPLER_MARKOV_JUMP) { cflags = p.ca_in[i]; Hc = ((const float*)p.Hc_in)[i]; }
+        if (lead && live && sampler == MJHMC_SAMPLER_MARKOV_JUMP) { cflags = p.ca_in[i]; Hc = ((const float*)p.Hc_in)[i]; }
 
         for (int it = 0; it < p.n_iter; ++it) {
             const unsigned long long attempt = p.attempt0 + (unsigned long long)it;
@@ -233,7 +246,7 @@ dense_tf32_kernel(const __grid_constant__ LaunchParams p, const float* __restric
             const float* Vc = (const float*)(it == 0 ? p.Vin : p.Vout);
             float* Xo = (float*)p.Xout;
             float* Vo = (float*)p.Vout;
-            const bool active = live && !failed;
+            const bool active = lead && live && !failed;
             if (sampler == MJHMC_SAMPLER_DISCRETE) {
                 if (tid == 0) s_coin = draw_coin(p, attempt) < p.p_r;
             }
@@ -248,65 +261,61 @@ dense_tf32_kernel(const __grid_constant__ LaunchParams p, const float* __restric
             const bool coin_fired = s_coin != 0;                       // read behind the barrier above
 
             for (int pass = first_pass; pass < 2; ++pass) {
-                // ---- load (x, +-v) of my particle; x goes to the A tiles split into hi / lo
+                // ---- load my slice of (x, +-v); x goes to the A tiles split into hi / lo
                 const float sign = pass == 0 ? -1.0f : 1.0f;
                 float ev = 0.0f;
 #pragma unroll
-                for (int kc = 0; kc < kTcMaxDim / 4; ++kc) {
-                    if (kc < kcores) {
+                for (int j = 0; j < kTcDimsPerThread; ++j) v[j] = 0.0f;
+#pragma unroll
+                for (int h = 0; h < kTcCoresPerThread; ++h) {
+                    const int kc = kc0 + h;
+                    if (kc < kc1) {
                         float xs[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int k = kc * 4 + j;
                             xs[j] = 0.0f;
-                            v[k] = 0.0f;
-                            if (live && k < d) { xs[j] = Xc[(long long)k * p.ld + i]; v[k] = sign * Vc[(long long)k * p.ld + i]; }
-                            ev += v[k] * v[k];
+                            v[h * 4 + j] = 0.0f;
+                            if (live && k < d) { xs[j] = Xc[(long long)k * p.ld + i]; v[h * 4 + j] = sign * Vc[(long long)k * p.ld + i]; }
+                            ev += v[h * 4 + j] * v[h * 4 + j];
                         }
                         const float4 hi = make_float4(tf32_hi(xs[0]), tf32_hi(xs[1]), tf32_hi(xs[2]), tf32_hi(xs[3]));
-                        const uint32_t off = a_row_offset(tid, kc);
+                        const uint32_t off = a_row_offset(m, kc);
                         *reinterpret_cast<float4*>(Ahi + off) = hi;
                         *reinterpret_cast<float4*>(Alo + off) = make_float4(xs[0] - hi.x, xs[1] - hi.y, xs[2] - hi.z, xs[3] - hi.w);
                     }
                 }
-                ev *= 0.5f;                                            // hmc_state.py:49-50
                 float e_start = 0.0f, e_end = 0.0f;
 
                 for (int st = 0; st <= L; ++st) {
                     tile_gradient();
-                    // ---- one sweep over my particle's gradient (TMEM -> registers, 64 dims per round trip)
+                    // ---- sweep over my slice of my particle's gradient (one TMEM round trip)
+                    float g[32];
+                    tmem_ld32(my_tmem, g);
 #pragma unroll
-                    for (int grp = 0; grp < (kTcMaxDim + 63) / 64; ++grp) {
-                        if (grp * 64 < KP) {
-                            float g[64];
-                            tmem_ld64(my_tmem + (uint32_t)(grp * 64), g);
+                    for (int h = 0; h < kTcCoresPerThread; ++h) {
+                        const int kc = kc0 + h;
+                        if (kc < kc1) {
+                            const uint32_t off = a_row_offset(m, kc);
+                            float4* ph = reinterpret_cast<float4*>(Ahi + off);
+                            float4* pl = reinterpret_cast<float4*>(Alo + off);
+                            const float4 xh = *ph, xl = *pl;
+                            float xs[4] = {xh.x + xl.x, xh.y + xl.y, xh.z + xl.z, xh.w + xl.w};
 #pragma unroll
-                            for (int h = 0; h < 16; ++h) {             // 4-dim core columns of this group
-                                const int kc = grp * 16 + h;
-                                if (kc * 4 < kTcMaxDim && kc < kcores) {
-                                    const uint32_t off = a_row_offset(tid, kc);
-                                    float4* ph = reinterpret_cast<float4*>(Ahi + off);
-                                    float4* pl = reinterpret_cast<float4*>(Alo + off);
-                                    const float4 xh = *ph, xl = *pl;
-                                    float xs[4] = {xh.x + xl.x, xh.y + xl.y, xh.z + xl.z, xh.w + xl.w};
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) {
-                                        const int k = kc * 4 + j;
-                                        const float gk = g[h * 4 + j];
-                                        if (st == 0) e_start += xs[j] * gk;
-                                        if (st == L) e_end += xs[j] * gk;
-                                        if (st > 0) v[k] += nhe * gk;  // second half kick of step st
-                                        if (st < L) {                  // first half kick + drift of step st+1
-                                            v[k] += nhe * gk;
-                                            xs[j] += eps * v[k];
-                                        }
-                                    }
-                                    if (st < L) {
-                                        const float4 hi = make_float4(tf32_hi(xs[0]), tf32_hi(xs[1]), tf32_hi(xs[2]), tf32_hi(xs[3]));
-                                        *ph = hi;
-                                        *pl = make_float4(xs[0] - hi.x, xs[1] - hi.y, xs[2] - hi.z, xs[3] - hi.w);
-                                    }
-                                }
+                            for (int j = 0; j < 4; ++j) {
+                                const float gk = g[h * 4 + j];
+                                float vv = v[h * 4 + j];
+                                e_start += st == 0 ? xs[j] * gk : 0.0f;
+                                e_end += st == L ? xs[j] * gk : 0.0f;
+                                vv += st > 0 ? nhe * gk : 0.0f;        // second half kick of step st
+                                vv += st < L ? nhe * gk : 0.0f;        // first half kick of step st+1
+                                xs[j] += st < L ? eps * vv : 0.0f;     // drift of step st+1
+                                v[h * 4 + j] = vv;
+                            }
+                            if (st < L) {
+                                const float4 hi = make_float4(tf32_hi(xs[0]), tf32_hi(xs[1]), tf32_hi(xs[2]), tf32_hi(xs[3]));
+                                *ph = hi;
+                                *pl = make_float4(xs[0] - hi.x, xs[1] - hi.y, xs[2] - hi.z, xs[3] - hi.w);
                             }
                         }
                     }
@@ -314,16 +323,27 @@ dense_tf32_kernel(const __grid_constant__ LaunchParams p, const float* __restric
                 if (L == 0) e_end = e_start;
                 float ev_end = 0.0f;
 #pragma unroll
-                for (int k = 0; k < kTcMaxDim; ++k) if (k < KP) ev_end += v[k] * v[k];
-                ev_end *= 0.5f;
-                const float h_start = 0.5f * e_start + ev;             // EX + EV, hmc_state.py:80-84
-                const float h_end = 0.5f * e_end + ev_end;
-                if (pass == 0) { if (need) { Hflf = h_end; n_exec += 1; } }
-                else { H = h_start; Hl = h_end; }
+                for (int j = 0; j < kTcDimsPerThread; ++j) ev_end += v[j] * v[j];   // slots beyond my dims hold 0
+                // ---- per-particle totals: the four slices meet in shared memory
+                s_red[0][q][m] = e_start; s_red[1][q][m] = e_end; s_red[2][q][m] = ev; s_red[3][q][m] = ev_end;
+                __syncthreads();
+                if (lead) {
+                    float t[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        t[r] = 0.0f;
+#pragma unroll
+                        for (int qq = 0; qq < kTcSplit; ++qq) t[r] += s_red[r][qq][m];
+                    }
+                    const float h_start = 0.5f * t[0] + 0.5f * t[2];   // EX + EV, hmc_state.py:80-84
+                    const float h_end = 0.5f * t[1] + 0.5f * t[3];
+                    if (pass == 0) { if (need) { Hflf = h_end; n_exec += 1; } }
+                    else { H = h_start; Hl = h_end; }
+                }
             }
             if (active) { n_E += 1; n_exec += 1; }
 
-            // ---- decision (same device code as the register-resident kernel)
+            // ---- decision by the lead thread of each particle (same device code as the register-resident kernel)
             unsigned int take = 0, flip = 0, refresh = 0, choice = 0;
             if (active) {
                 if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
@@ -353,45 +373,56 @@ dense_tf32_kernel(const __grid_constant__ LaunchParams p, const float* __restric
                     n_l += (acc && fl); n_f += (fl && !acc); n_fl += (acc && !fl); n_r += refresh;
                 }
             }
-            const bool ok = active && !failed;
+            if (lead) s_code[m] = take | (flip << 2) | (refresh << 3) | ((active && !failed) ? 16u : 0u);
+            __syncthreads();
+            const unsigned int code = s_code[m];
+            const unsigned int tk = code & 3u;
+            const bool fp = code & 4u, rf = code & 8u, ok = code & 16u;
 
-            // ---- apply: my particle's new state goes to the output arrays
+            // ---- apply: my slice of my particle's new state goes to the output arrays
             if (live) {
 #pragma unroll
-                for (int k = 0; k < kTcMaxDim; ++k) {
-                    if (k < d) {
-                        const long long o = (long long)k * p.ld + i;
-                        float xn, vn;
-                        if (ok && take) {
-                            const uint32_t off = a_row_offset(tid, k >> 2) + (uint32_t)(k & 3) * 4u;
-                            xn = *reinterpret_cast<const float*>(Ahi + off) + *reinterpret_cast<const float*>(Alo + off);
-                            vn = take == 1 ? v[k] : -v[k];
-                        } else {
-                            xn = Xc[o];
-                            vn = Vc[o];
+                for (int h = 0; h < kTcCoresPerThread; ++h) {
+                    const int kc = kc0 + h;
+                    if (kc < kc1) {
+                        const uint32_t off = a_row_offset(m, kc);
+                        const float4 xh = *reinterpret_cast<const float4*>(Ahi + off), xl = *reinterpret_cast<const float4*>(Alo + off);
+                        const float xt[4] = {xh.x + xl.x, xh.y + xl.y, xh.z + xl.z, xh.w + xl.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int k = kc * 4 + j;
+                            if (k < d) {
+                                const long long o = (long long)k * p.ld + i;
+                                float xn, vn;
+                                if (ok && tk) { xn = xt[j]; vn = tk == 1 ? v[h * 4 + j] : -v[h * 4 + j]; }
+                                else { xn = Xc[o]; vn = Vc[o]; }
+                                if (ok && fp) vn = -vn;
+                                if (ok && rf) {
+                                    double z0, z1;
+                                    normal_pair(p, i, attempt, k >> 1, d, z0, z1);
+                                    vn = vn * (float)p.r_keep + (float)((k & 1) ? z1 : z0) * (float)p.r_mix;   // hmc_state.py:126
+                                }
+                                Xo[o] = xn;
+                                Vo[o] = vn;
+                                if (ok && p.samples) ((float*)p.samples)[(long long)k * p.s_stride_k + (long long)it * p.s_stride_it + i] = xn;
+                            }
                         }
-                        if (ok && flip) vn = -vn;
-                        if (ok && refresh) {
-                            double z0, z1;
-                            normal_pair(p, i, attempt, k >> 1, d, z0, z1);
-                            vn = vn * (float)p.r_keep + (float)((k & 1) ? z1 : z0) * (float)p.r_mix;   // hmc_state.py:126
-                        }
-                        Xo[o] = xn;
-                        Vo[o] = vn;
-                        if (ok && p.samples) ((float*)p.samples)[(long long)k * p.s_stride_k + (long long)it * p.s_stride_it + i] = xn;
                     }
                 }
-                if (ok) {
+                if (lead && ok) {
                     if (p.dwell) p.dwell[(long long)it * p.n + i] = dwell;
                     if (p.choice) p.choice[(long long)it * p.n + i] = (uint8_t)choice;
                 }
             }
+            __syncthreads();                       // s_code / s_red / the A tiles are reused by the next iteration
         }
         if (live) {
-            if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) { p.ca_out[i] = (uint8_t)cflags; ((float*)p.Hc_out)[i] = Hc; }
-            if (p.dwell_last && sampler != MJHMC_SAMPLER_DISCRETE) p.dwell_last[i] = dwell;
+            if (lead) {
+                if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) { p.ca_out[i] = (uint8_t)cflags; ((float*)p.Hc_out)[i] = Hc; }
+                if (p.dwell_last && sampler != MJHMC_SAMPLER_DISCRETE) p.dwell_last[i] = dwell;
+            }
             if (p.n_iter == 0) {
-                for (int k = 0; k < d; ++k) {
+                for (int k = kc0 * 4; k < min(d, kc1 * 4); ++k) {
                     ((float*)p.Xout)[(long long)k * p.ld + i] = ((const float*)p.Xin)[(long long)k * p.ld + i];
                     ((float*)p.Vout)[(long long)k * p.ld + i] = ((const float*)p.Vin)[(long long)k * p.ld + i];
                 }
@@ -444,7 +475,7 @@ cudaError_t launch_dense_tf32(const LaunchParams& p, cudaStream_t stream) {
     }
     cudaError_t e = cudaFuncSetAttribute(dense_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    long long tiles = (p.n + kTcThreads - 1) / kTcThreads;
+    long long tiles = (p.n + kTcTile - 1) / kTcTile;
     if (tiles > sms) tiles = sms;
     dense_tf32_kernel<<<(unsigned)tiles, kTcThreads, smem, stream>>>(p, (const float*)p.a1);
     return cudaGetLastError();
