@@ -55,6 +55,12 @@ WORKLOADS = {
     # HBM-bound points of the fused leapfrog (one iteration per launch, L = 1)
     "testgauss2d_control_L1": dict(dist="TestGaussian", ndims=2, n=16_000_000, sampler="ControlHMC",
                                    epsilon=0.5, beta=0.1, L=1, iters=1, source="HBM roofline point"),
+    "gauss10d_control_L1": dict(dist="DiagGaussian", ndims=10, n=8_000_000, sampler="ControlHMC",
+                                epsilon=0.5, beta=0.1, L=1, iters=1, source="HBM roofline point, diagonal Gaussian log_cond=1"),
+    "gauss16d_control_L1": dict(dist="DiagGaussian", ndims=16, n=4_000_000, sampler="ControlHMC",
+                                epsilon=0.5, beta=0.1, L=1, iters=1, source="HBM roofline point, diagonal Gaussian log_cond=1"),
+    "gauss16d_control_L1_f32": dict(dist="DiagGaussian", ndims=16, n=8_000_000, sampler="ControlHMC", dtype="float32",
+                                    epsilon=0.5, beta=0.1, L=1, iters=1, source="HBM roofline point, fp32 states"),
     "roughwell2d_control_L1": dict(dist="RoughWell", ndims=2, n=16_000_000, sampler="ControlHMC",
                                    epsilon=0.5, beta=0.1, L=1, iters=1, source="HBM roofline point"),
 }
@@ -74,7 +80,8 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def algorithmic_bytes_per_launch(w, S=8):
+def algorithmic_bytes_per_launch(w, S=None):
+    S = S or (4 if w.get("dtype") == "float32" else 8)
     """DESIGN.md 'Algorithmic traffic': per particle, one launch of `iters` iterations reads X,V,
     writes X,V, writes one sample column per iteration (+ dwell time of the last iteration for the
     jump samplers; + FLF cache scalar and flag read and written for MarkovJumpHMC)."""
@@ -96,6 +103,8 @@ def _oracle_energy(w):
         return orc.RoughWellEnergy(100, 4)
     if w["dist"] == "TestGaussian":
         return orc.TestGaussianEnergy(1.0)
+    if w["dist"] == "DiagGaussian":
+        return orc.GaussianEnergy.log_conditioned(w["ndims"], 1)
     if w["dist"] == "Funnel":
         return orc.FunnelEnergy(3.0)
     if w["dist"] == "GaussianRot":
@@ -233,6 +242,8 @@ def make_sampler(w, rank, dtype=None, seed=2024):
         dist = D.RoughWell(ndims=d, nbatch=n)
     elif w["dist"] == "TestGaussian":
         dist = D.TestGaussian(ndims=d, nbatch=n)
+    elif w["dist"] == "DiagGaussian":
+        dist = D.Gaussian(ndims=d, nbatch=8, log_conditioning=1)
     elif w["dist"] == "Funnel":
         dist = D.Funnel(scale=3.0, ndims=d, nbatch=n)
     elif w["dist"] == "GaussianRot":
@@ -318,11 +329,7 @@ def run_b200(args, w):
     e2e_steps = max(1, min(args.steps, 5))
 
     def e2e_step():
-        st = HMCState.__new__(HMCState)
-        st.parent, st.X, st.V, st.nbatch = sampler, Xh, Vh, Xh.shape[1]
-        st.cache_active = np.zeros(st.nbatch, dtype=bool)
-        st.H_cache = np.zeros(st.nbatch)
-        sampler.state = st                                   # H2D at the next launch
+        sampler.state = HMCState.from_buffers(sampler, Xh, Vh)   # H2D from pinned memory at the next launch
         return sampler.sample(iters)                         # D2H of (ndims, iters * n)
 
     for _ in range(2):                                       # warm the pinned staging buffers (not timed)

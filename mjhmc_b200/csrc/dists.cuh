@@ -14,18 +14,9 @@
 
 namespace mjhmc {
 
-template <typename T> __device__ __forceinline__ T t_sin(T x);
-template <> __device__ __forceinline__ double t_sin<double>(double x) { return sin(x); }
-template <> __device__ __forceinline__ float t_sin<float>(float x) { return sinf(x); }
-template <typename T> __device__ __forceinline__ T t_sinpi(T x);
-template <> __device__ __forceinline__ double t_sinpi<double>(double x) { return sinpi(x); }
-template <> __device__ __forceinline__ float t_sinpi<float>(float x) { return sinpif(x); }
 template <typename T> __device__ __forceinline__ T t_cospi(T x);
 template <> __device__ __forceinline__ double t_cospi<double>(double x) { return cospi(x); }
 template <> __device__ __forceinline__ float t_cospi<float>(float x) { return cospif(x); }
-template <typename T> __device__ __forceinline__ T t_cos(T x);
-template <> __device__ __forceinline__ double t_cos<double>(double x) { return cos(x); }
-template <> __device__ __forceinline__ float t_cos<float>(float x) { return cosf(x); }
 template <typename T> __device__ __forceinline__ T t_exp(T x);
 template <> __device__ __forceinline__ double t_exp<double>(double x) { return exp(x); }
 template <> __device__ __forceinline__ float t_exp<float>(float x) { return expf(x); }

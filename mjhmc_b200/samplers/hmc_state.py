@@ -22,6 +22,18 @@ class HMCState(object):
                              else np.array(cache_active, dtype=bool))
         self.H_cache = np.zeros(self.nbatch) if H_cache is None else np.array(H_cache, dtype=np.float64)
 
+    @classmethod
+    def from_buffers(cls, parent, X, V, cache_active=None, H_cache=None):
+        """B200 extension: wrap existing host buffers (numpy arrays or pinned torch tensors) without copying;
+        assigning the result to ``sampler.state`` uploads them at the next launch."""
+        st = cls.__new__(cls)
+        st.parent, st.X, st.V = parent, X, V
+        st.nbatch = X.shape[1]
+        st.active_idx = np.arange(st.nbatch)
+        st.cache_active = np.zeros(st.nbatch, dtype=bool) if cache_active is None else cache_active
+        st.H_cache = np.zeros(st.nbatch) if H_cache is None else H_cache
+        return st
+
     # derived arrays (hmc_state.py:28-39, 46-53), evaluated on the device, not counted
     @property
     def EX(self):

@@ -534,8 +534,50 @@ class HMCBase(object):
         """
         if num_steps is not None:
             n_samples = num_steps
+        return self._sample_plain(n_samples, preserve_order)
+
+    def _sample_plain(self, n_samples, preserve_order):
+        """n iterations, every state recorded (markov_jump_hmc.py:166-173 / :331-338)."""
+        if not preserve_order and self._pipeline_chunks(n_samples) > 1:
+            return self._sample_pipelined(n_samples)
         S = self._advance(n_samples)[0]
         return self._to_host(S, preserve_order)
+
+    # -- host transfer ------------------------------------------------------------------------------
+    PIPELINE_MIN_BYTES = 64 << 20      # below this one launch + one copy is cheaper than a pipeline
+
+    def _pipeline_chunks(self, n_samples):
+        eng = self._engine
+        if eng.device.type != "cuda" or n_samples < 8:
+            return 1
+        nbytes = self.ndims * n_samples * self.nbatch * torch.empty((), dtype=eng.tdtype).element_size()
+        return min(8, n_samples // 4) if nbytes >= self.PIPELINE_MIN_BYTES else 1
+
+    def _sample_pipelined(self, n_samples):
+        """sample() for large outputs: the iterations run in a few launches and the device->host copy of
+        chunk c (side stream, pinned destination) overlaps the kernel of chunk c+1."""
+        eng = self._engine
+        chunks = self._pipeline_chunks(n_samples)
+        d, N = self.ndims, self.nbatch
+        out = torch.empty((d, n_samples, N), dtype=eng.tdtype, pin_memory=True)
+        if not hasattr(eng, "copy_stream"):
+            eng.copy_stream = torch.cuda.Stream(device=eng.device)
+        main = torch.cuda.current_stream(eng.device)
+        bounds = [n_samples * c // chunks for c in range(chunks + 1)]
+        keep = []
+        for c in range(chunks):
+            c0, c1 = bounds[c], bounds[c + 1]
+            S = self._advance(c1 - c0)[0]                  # returns after the launch completed (counter read)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(eng.copy_stream):
+                eng.copy_stream.wait_event(ready)
+                for k in range(d):                         # contiguous (c1-c0)*N runs: plain async memcpys
+                    out[k, c0:c1, :].copy_(S[k], non_blocking=True)
+            S.record_stream(eng.copy_stream)
+            keep.append(S)
+        eng.copy_stream.synchronize()
+        return out.numpy().reshape(d, n_samples * N).astype(np.float64, copy=False)
 
     def _d2h(self, t):
         """Device tensor -> fresh host numpy array through a pinned staging tensor (torch's caching
@@ -623,7 +665,7 @@ class ContinuousTimeHMC(HMCBase):
         if num_steps is not None:
             n_samples = num_steps
         if not self.resample:
-            return self._to_host(self._advance(n_samples)[0], preserve_order)
+            return self._sample_plain(n_samples, preserve_order)
         eng = self._engine
         # 1 + n iterations; sample k is paired with the dwelling time recorded before iteration k+1
         S, dwell, _ = self._advance(n_samples + 1, want_dwell=True)

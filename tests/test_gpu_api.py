@@ -243,3 +243,22 @@ def test_moments_ill_conditioned_gaussian(kind, dtype):
         X = s.sample(300)
     assert np.linalg.norm(np.cov(X) - target) < .05 * 10, (kind, np.cov(X))
     assert np.linalg.norm(np.cov(X) - target) / np.linalg.norm(target) < .05
+
+
+def test_pipelined_sample_equals_single_launch():
+    """Large outputs are sampled in a few launches with the device->host copy overlapping the next launch;
+    the result must not depend on the chunking (counter-based streams, persistent state)."""
+    from mjhmc_b200.misc.distributions import RoughWell
+    from mjhmc_b200.samplers.markov_jump_hmc import MarkovJumpHMC
+    rs = np.random.RandomState(17)
+    X0, V0 = rs.randn(2, 300) * 3, rs.randn(2, 300)
+    hp = dict(epsilon=0.4, beta=0.3, num_leapfrog_steps=3, seed=12, resample=False)
+    outs = []
+    for min_bytes in (1 << 60, 0):
+        dist = helpers.pin_init(RoughWell(2, 300, scale1=5, scale2=4), X0)
+        s = MarkovJumpHMC(distribution=dist, V=V0, **hp)
+        s.PIPELINE_MIN_BYTES = min_bytes
+        outs.append((s.sample(37), _counters(s, dist), s._engine.launches))
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    assert outs[0][1] == outs[1][1]
+    assert outs[0][2] == 1 and outs[1][2] == 8
