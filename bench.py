@@ -63,6 +63,30 @@ WORKLOADS = {
                                     epsilon=0.5, beta=0.1, L=1, iters=1, source="HBM roofline point, fp32 states"),
     "roughwell2d_control_L1": dict(dist="RoughWell", ndims=2, n=16_000_000, sampler="ControlHMC",
                                    epsilon=0.5, beta=0.1, L=1, iters=1, source="HBM roofline point"),
+    # the same points through the streaming kernel (TMA ring, csrc/stream_separable.cuh)
+    "testgauss2d_control_L1_stream": dict(dist="TestGaussian", ndims=2, n=16_000_000, sampler="ControlHMC", kernel="stream",
+                                          epsilon=0.5, beta=0.1, L=1, iters=1, source="HBM roofline point, streaming kernel"),
+    "roughwell2d_control_L1_stream": dict(dist="RoughWell", ndims=2, n=16_000_000, sampler="ControlHMC", kernel="stream",
+                                          epsilon=0.5, beta=0.1, L=1, iters=1, source="HBM roofline point, streaming kernel"),
+    "gauss10d_control_L1_stream": dict(dist="DiagGaussian", ndims=10, n=8_000_000, sampler="ControlHMC", kernel="stream",
+                                       epsilon=0.5, beta=0.1, L=1, iters=1,
+                                       source="HBM roofline point, diagonal Gaussian log_cond=1, streaming kernel"),
+    "gauss16d_control_L1_stream": dict(dist="DiagGaussian", ndims=16, n=4_000_000, sampler="ControlHMC", kernel="stream",
+                                       epsilon=0.5, beta=0.1, L=1, iters=1,
+                                       source="HBM roofline point, diagonal Gaussian log_cond=1, streaming kernel"),
+    "gauss16d_control_L1_f32_stream": dict(dist="DiagGaussian", ndims=16, n=8_000_000, sampler="ControlHMC", dtype="float32",
+                                           kernel="stream", epsilon=0.5, beta=0.1, L=1, iters=1,
+                                           source="HBM roofline point, fp32 states, streaming kernel"),
+    # configs[2] as the reference builds it: Gaussian(ndims=100) is DIAGONAL (distributions.py:257-263)
+    "gauss100d_diag_mjhmc": dict(dist="DiagGaussian", log_cond=6, ndims=100, n=1_000_000, sampler="MarkovJumpHMC",
+                                 epsilon=1.4581446647644043, beta=0.009999999776482582, L=25, iters=1,
+                                 source="search/MJHMC_log_gauss/params_2.json; reference default diagonal J; streaming kernel"),
+    "gauss100d_diag_mjhmc_x8": dict(dist="DiagGaussian", log_cond=6, ndims=100, n=1_000_000, sampler="MarkovJumpHMC",
+                                    epsilon=1.4581446647644043, beta=0.009999999776482582, L=25, iters=8,
+                                    source="search/MJHMC_log_gauss/params_2.json; reference default diagonal J; streaming kernel"),
+    "gauss100d_diag_control_L1": dict(dist="DiagGaussian", log_cond=6, ndims=100, n=1_000_000, sampler="ControlHMC",
+                                      epsilon=0.0010000000474974513, beta=0.009999999776482582, L=1, iters=1,
+                                      source="search/control_log_gauss/params.json; reference default diagonal J; streaming kernel"),
 }
 DEFAULT_WORKLOAD = "roughwell2d_mjhmc"
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full captures (profiles/)
@@ -104,7 +128,7 @@ def _oracle_energy(w):
     if w["dist"] == "TestGaussian":
         return orc.TestGaussianEnergy(1.0)
     if w["dist"] == "DiagGaussian":
-        return orc.GaussianEnergy.log_conditioned(w["ndims"], 1)
+        return orc.GaussianEnergy.log_conditioned(w["ndims"], w.get("log_cond", 1))
     if w["dist"] == "Funnel":
         return orc.FunnelEnergy(3.0)
     if w["dist"] == "GaussianRot":
@@ -139,6 +163,8 @@ def _init_cloud(w, n, seed):
     elif w["dist"] == "GaussianRot":
         wv, Q = np.linalg.eigh(_rotated_J(d))
         X = Q.dot((1. / np.sqrt(wv)).reshape((-1, 1)) * rs.randn(d, n))
+    elif w["dist"] == "DiagGaussian" and w.get("log_cond", 1) != 1:
+        X = rs.randn(d, n) / np.sqrt(10 ** np.linspace(-w["log_cond"], 0, d)).reshape(-1, 1)   # distributions.py:277
     else:
         X = rs.randn(d, n)
     return X, rs.randn(d, n)
@@ -243,7 +269,7 @@ def make_sampler(w, rank, dtype=None, seed=2024):
     elif w["dist"] == "TestGaussian":
         dist = D.TestGaussian(ndims=d, nbatch=n)
     elif w["dist"] == "DiagGaussian":
-        dist = D.Gaussian(ndims=d, nbatch=8, log_conditioning=1)
+        dist = D.Gaussian(ndims=d, nbatch=8, log_conditioning=w.get("log_cond", 1))
     elif w["dist"] == "Funnel":
         dist = D.Funnel(scale=3.0, ndims=d, nbatch=n)
     elif w["dist"] == "GaussianRot":
@@ -257,6 +283,8 @@ def make_sampler(w, rank, dtype=None, seed=2024):
     X0, V0 = _init_cloud(w, n, 1000 + rank)
     dist.gen_init_X = lambda: setattr(dist, "Xinit", X0)
     kw = dict(resample=False) if w["sampler"] in ("ContinuousTimeHMC", "MarkovJumpHMC") else {}
+    if w.get("kernel"):
+        kw["kernel"] = w["kernel"]
     s = getattr(S, w["sampler"])(distribution=dist, epsilon=w["epsilon"], beta=w["beta"], num_leapfrog_steps=w["L"],
                                  V=V0, dtype=dtype, seed=seed, particle_offset=rank * n, **kw)
     return s, dist, X0, V0
@@ -299,6 +327,7 @@ def run_b200(args, w):
     g0, x0, launches0 = dist.dEdX_count, sampler.grad_evals_executed, eng.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    eng.kernel_events = []                    # CUDA events right around each sampler-kernel launch (roofline)
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.fill_(float(k))                 # evict the state from L2 between timed steps
@@ -310,6 +339,8 @@ def run_b200(args, w):
     t_wall = time.perf_counter() - t_wall0
     clk = clocks.stop() if rank == 0 else None
     ms = sum(a.elapsed_time(b) for a, b in ev)
+    kernel_ms = [a.elapsed_time(b) for a, b in eng.kernel_events]
+    eng.kernel_events = None
     grads = sampler.grad_evals_executed - x0          # leapfrog steps actually integrated on the device
     grads_ref = dist.dEdX_count - g0                  # the reference's dEdX_count accounting
     launches = eng.launches - launches0
@@ -354,7 +385,8 @@ def run_b200(args, w):
     if rank == 0:
         peak, peak_src = measured_peak()
         alg = algorithmic_bytes_per_launch(w)
-        launch_ms = ms_max / args.steps
+        # roofline: the sampler kernel alone (a step also resets and reads back the counter block)
+        launch_ms = float(np.mean(kernel_ms)) if kernel_ms else ms_max / args.steps
         achieved = alg / (launch_ms * 1e-3) / 1e9
         if w["dist"] in ("GaussianRot", "ProductOfT"):
             # dense-contraction energies: algorithmic flops per leapfrog step = 2 d^2 (S x) resp. 4 d nb (W^T x, W G)
@@ -374,7 +406,9 @@ def run_b200(args, w):
                         "hbm_gbs": achieved, "note": "ncu sm__pipe_tensor_cycles_active in profiles/r1_dense_*.txt"}
         else:
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": TRAFFIC.get(args.workload), "peak_source": peak_src, "kernel": "fused_sample_kernel",
+                        "traffic": TRAFFIC.get(args.workload), "peak_source": peak_src,
+                        "kernel": "stream_sample_kernel" if (w.get("kernel") == "stream" or w["ndims"] > 16)
+                                  else "fused_sample_kernel",
                         "algorithmic_bytes_per_launch": alg, "launch_ms": launch_ms,
                         "note": ("L=%d leapfrog steps per sample: the kernel is FP64-issue bound "
                                  "(ncu sm__pipe_fp64_cycles_active 71%%, DESIGN.md 3.1), not HBM bound" % w["L"])

@@ -144,6 +144,25 @@ int mjhmc_sample_fused(const mjhmc_dist *dist, const mjhmc_hp *hp, const mjhmc_r
                        const mjhmc_state *in, const mjhmc_state *out,
                        int32_t n_iter, const mjhmc_outputs *o, void *stream);
 
+/* Same contract as mjhmc_sample_fused, forced onto the streaming kernel for SEPARABLE energies
+ * (MJHMC_DIST_TEST_GAUSSIAN, _DIAG_GAUSSIAN, _ROUGH_WELL; ndims <= 128): persistent CTAs walk particle tiles whose
+ * X / V boxes arrive through a TMA ring, several threads share one particle (the dims of hmc_state.py:86-91
+ * evolve independently; only the energy sums of :46-50 couple them).  mjhmc_sample_fused picks it by itself
+ * when ndims > 16; call it directly for short trajectories (L of a few steps), where the path is HBM-bound.
+ * `in` and `out` must not alias unless they are identical.  mjhmc_stream_supported: 1 if a kernel exists.
+ * mjhmc_stream_set_tma(0) forces the non-TMA loader (it is also taken when X / V are not 16-byte aligned
+ * or ld * sizeof(dtype) is not a multiple of 16). */
+int mjhmc_stream_supported(const mjhmc_dist *dist);
+int mjhmc_sample_stream(const mjhmc_dist *dist, const mjhmc_hp *hp, const mjhmc_rng *rng,
+                        const mjhmc_state *in, const mjhmc_state *out,
+                        int32_t n_iter, const mjhmc_outputs *o, void *stream);
+void mjhmc_stream_set_tma(int32_t enabled);
+/* launch geometry of the calling thread's last streaming launch:
+ * {TMA used, ring stages, grid, CTAs per SM, warps per particle column, dims per thread, dynamic smem bytes} */
+void mjhmc_stream_last_launch(int64_t *out7_host);
+/* developer probe: resident 256-thread CTAs per SM of a trivial kernel with `smem_bytes` of dynamic shared memory */
+int mjhmc_stream_probe_blocks(int64_t smem_bytes);
+
 /* Replaces Distribution.E_val / dEdX_val (distributions.py:62-81) for the built-in
  * energies and HMCState.update_EV (hmc_state.py:49-50).  E, EV: (n,) dtype; G: (ndims, n). */
 int mjhmc_energy(const mjhmc_dist *dist, const void *X, int64_t n, int64_t ld, void *E, void *stream);

@@ -62,6 +62,12 @@ SYMBOLS = {
     "mjhmc_fused_supported": (C.c_int, [_P(Dist)]),
     "mjhmc_sample_fused": (C.c_int, [_P(Dist), _P(HP), _P(RNG), _P(State), _P(State), C.c_int32, _P(Outputs),
                                      C.c_void_p]),
+    "mjhmc_stream_supported": (C.c_int, [_P(Dist)]),
+    "mjhmc_sample_stream": (C.c_int, [_P(Dist), _P(HP), _P(RNG), _P(State), _P(State), C.c_int32, _P(Outputs),
+                                      C.c_void_p]),
+    "mjhmc_stream_set_tma": (None, [C.c_int32]),
+    "mjhmc_stream_last_launch": (None, [_P(C.c_int64)]),
+    "mjhmc_stream_probe_blocks": (C.c_int, [C.c_int64]),
     "mjhmc_energy": (C.c_int, [_P(Dist), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "mjhmc_gradient": (C.c_int, [_P(Dist), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "mjhmc_kinetic": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -22,17 +22,23 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-Xcompiler", "-fPIC"]
 
 DIM_GROUPS = [(1, 2), (3, 4), (6, 8), (10, 16)]
+STREAM_DTS = [2, 4, 6, 8, 10, 13, 16]     # dims per thread of the streaming kernels (one unit each)
 
 
 def _units():
     units = []
-    for name in ("api", "unfused", "analysis", "dense", "dense_tc"):
+    for name in ("api", "unfused", "analysis", "dense", "dense_tc", "stream"):
         units.append((name, os.path.join(CSRC, name + ".cu"), []))
     for tname, ctype in (("f64", "double"), ("f32", "float")):
         for g, (da, db) in enumerate(DIM_GROUPS):
             tag = "%s_g%d" % (tname, g)
             units.append(("fused_inst_" + tag, os.path.join(CSRC, "fused_inst.cu"),
                           ["-DMJ_T=" + ctype, "-DMJ_TAG=" + tag, "-DMJ_DA=%d" % da, "-DMJ_DB=%d" % db]))
+    for tname, ctype in (("f64", "double"), ("f32", "float")):
+        for g, da in enumerate(STREAM_DTS):
+            tag = "%s_g%d" % (tname, g)
+            units.append(("stream_inst_" + tag, os.path.join(CSRC, "stream_inst.cu"),
+                          ["-DMJ_T=" + ctype, "-DMJ_TAG=" + tag, "-DMJ_DA=%d" % da]))
     return units
 
 

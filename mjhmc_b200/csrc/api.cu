@@ -8,6 +8,7 @@
 #include "unfused.h"
 #include "analysis.h"
 #include "dense.h"
+#include "stream.h"
 
 namespace mjhmc {
 fused_launch_fn find_fused_f64_g0(int, int); fused_launch_fn find_fused_f64_g1(int, int);
@@ -126,14 +127,24 @@ int mjhmc_fused_supported(const mjhmc_dist* dist) {
     if (check_dist(dist)) return 0;
     if (is_elementwise(dist->kind)) {
         const int D = fused_template_dim(dist->ndims);
-        return D && find_fused(dist->dtype, dist->kind, D) ? 1 : 0;
+        if (D && find_fused(dist->dtype, dist->kind, D)) return 1;
+        return stream_supported(dist->dtype, dist->kind, dist->ndims) ? 1 : 0;
     }
     return dense_supported(dist->dtype, dist->kind, dist->ndims, dist->nbasis) ? 1 : 0;
 }
 
-int mjhmc_sample_fused(const mjhmc_dist* dist, const mjhmc_hp* hp, const mjhmc_rng* rng,
+int mjhmc_stream_supported(const mjhmc_dist* dist) {
+    if (check_dist(dist)) return 0;
+    return stream_supported(dist->dtype, dist->kind, dist->ndims) ? 1 : 0;
+}
+
+void mjhmc_stream_set_tma(int32_t enabled) { stream_set_tma(enabled); }
+int mjhmc_stream_probe_blocks(int64_t smem_bytes) { return stream_probe_blocks(smem_bytes); }
+void mjhmc_stream_last_launch(int64_t* out7_host) { if (out7_host) stream_last_launch((long long*)out7_host); }
+
+static int sample_impl(const mjhmc_dist* dist, const mjhmc_hp* hp, const mjhmc_rng* rng,
                        const mjhmc_state* in, const mjhmc_state* out, int32_t n_iter,
-                       const mjhmc_outputs* o, void* stream_) {
+                       const mjhmc_outputs* o, void* stream_, bool force_stream) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (check_dist(dist)) return -1;
     if (!hp || !rng || !in || !out || !o) return fail("NULL argument");
@@ -160,15 +171,34 @@ int mjhmc_sample_fused(const mjhmc_dist* dist, const mjhmc_hp* hp, const mjhmc_r
     p.Hc_in = in->H_cache; p.Hc_out = out->H_cache; p.ca_in = in->cache_active; p.ca_out = out->cache_active;
     p.n = in->n; p.ld = in->ld; p.n_iter = n_iter;
     if (p.n == 0) return 0;
+    if (force_stream) {
+        if (!stream_supported(dist->dtype, dist->kind, dist->ndims))
+            return fail("no streaming kernel for this distribution / ndims (separable energies, ndims <= 128)");
+        return check(launch_stream_kernel(dist->dtype, dist->kind, p, stream), "stream_sample_kernel");
+    }
     if (is_elementwise(dist->kind)) {
         const int D = fused_template_dim(dist->ndims);
         fused_launch_fn fn = D ? find_fused(dist->dtype, dist->kind, D) : nullptr;
-        if (!fn) return fail("no fused kernel for this distribution / ndims (use the unfused path)");
-        return check(fn(p, stream), "fused_sample_kernel");
+        if (fn) return check(fn(p, stream), "fused_sample_kernel");
+        if (stream_supported(dist->dtype, dist->kind, dist->ndims))
+            return check(launch_stream_kernel(dist->dtype, dist->kind, p, stream), "stream_sample_kernel");
+        return fail("no fused kernel for this distribution / ndims (use the unfused path)");
     }
     if (!dense_supported(dist->dtype, dist->kind, dist->ndims, dist->nbasis))
         return fail("no fused dense kernel for this distribution / shape (use the unfused path)");
     return check(launch_dense(dist->dtype, dist->kind, p, stream), "dense_sample_kernel");
+}
+
+int mjhmc_sample_fused(const mjhmc_dist* dist, const mjhmc_hp* hp, const mjhmc_rng* rng,
+                       const mjhmc_state* in, const mjhmc_state* out, int32_t n_iter,
+                       const mjhmc_outputs* o, void* stream) {
+    return sample_impl(dist, hp, rng, in, out, n_iter, o, stream, false);
+}
+
+int mjhmc_sample_stream(const mjhmc_dist* dist, const mjhmc_hp* hp, const mjhmc_rng* rng,
+                        const mjhmc_state* in, const mjhmc_state* out, int32_t n_iter,
+                        const mjhmc_outputs* o, void* stream) {
+    return sample_impl(dist, hp, rng, in, out, n_iter, o, stream, true);
 }
 
 int mjhmc_energy(const mjhmc_dist* dist, const void* X, int64_t n, int64_t ld, void* E, void* stream) {

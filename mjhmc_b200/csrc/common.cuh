@@ -144,49 +144,119 @@ __device__ __forceinline__ double jump_rate(double ediff) { return sqrt(exp(edif
 struct Decision { unsigned int choice; double dwell; bool fail; };
 
 // MarkovJumpHMC (markov_jump_hmc.py:366-396): choice 0 = L, 1 = F, 2 = R.
-// ediff_l = H - H_L, ediff_flf = H - H_FLF.
-MJ_COLD Decision decide_mj(const LaunchParams& p, long long i, unsigned long long attempt,
-                                              double ediff_l, double ediff_flf) {
+// ediff_l = H - H_L, ediff_flf = H - H_FLF.  The *_u forms take the uniforms of the attempt as arguments
+// (the streaming kernel draws them before the trajectory so the Philox rounds overlap the fp64 work).
+__device__ __forceinline__ Decision decide_mj_u(double p_r, double u0, double u1, double u2,
+                                                double ediff_l, double ediff_flf) {
     Decision dc; dc.choice = 0; dc.dwell = 0.0; dc.fail = false;
     const double rl = jump_rate(ediff_l);
     const double rflf = jump_rate(ediff_flf);
     if (!(isfinite(rl) && isfinite(rflf))) { dc.fail = true; return dc; }
     const double rf = rflf - (rl < rflf ? rl : rflf);              // :368
-    const Uniform3 u = draw_uniforms(p, i, attempt, p.p_r != 0.0);
-    const double tl = exp_draw(rl, u.u0);
-    const double tf = exp_draw(rf, u.u1);
-    const double tr = exp_draw(p.p_r, u.u2);
+    const double tl = exp_draw(rl, u0);
+    const double tf = exp_draw(rf, u1);
+    const double tr = exp_draw(p_r, u2);
     dc.dwell = tl;                                                 // min_idx([l, f, r]): first minimum wins
     if (tf < dc.dwell) { dc.choice = 1; dc.dwell = tf; }
     if (tr < dc.dwell) { dc.choice = 2; dc.dwell = tr; }
     return dc;
 }
+MJ_COLD Decision decide_mj(const LaunchParams& p, long long i, unsigned long long attempt,
+                                              double ediff_l, double ediff_flf) {
+    const Uniform3 u = draw_uniforms(p, i, attempt, p.p_r != 0.0);
+    return decide_mj_u(p.p_r, u.u0, u.u1, u.u2, ediff_l, ediff_flf);
+}
 
 // ContinuousTimeHMC (markov_jump_hmc.py:261-275): choice 0 = F, 1 = FL, 2 = R.
-MJ_COLD Decision decide_ct(const LaunchParams& p, long long i, unsigned long long attempt,
-                                              double ediff_fl) {
+__device__ __forceinline__ Decision decide_ct_u(double p_r, double u0, double u1, double u2, double ediff_fl) {
     Decision dc; dc.choice = 0; dc.dwell = 0.0; dc.fail = false;
     const double rfl = jump_rate(ediff_fl);
     if (!isfinite(rfl)) { dc.fail = true; return dc; }
-    const Uniform3 u = draw_uniforms(p, i, attempt, p.p_r != 0.0);
-    const double tfl = exp_draw(rfl, u.u0);
-    const double tf = exp_draw(1.0, u.u1);
-    const double tr = exp_draw(p.p_r, u.u2);
+    const double tfl = exp_draw(rfl, u0);
+    const double tf = exp_draw(1.0, u1);
+    const double tr = exp_draw(p_r, u2);
     dc.dwell = tf;                                                 // min_idx([f, fl, r]) :271
     if (tfl < dc.dwell) { dc.choice = 1; dc.dwell = tfl; }
     if (tr < dc.dwell) { dc.choice = 2; dc.dwell = tr; }
     return dc;
 }
+MJ_COLD Decision decide_ct(const LaunchParams& p, long long i, unsigned long long attempt,
+                                              double ediff_fl) {
+    const Uniform3 u = draw_uniforms(p, i, attempt, p.p_r != 0.0);
+    return decide_ct_u(p.p_r, u.u0, u.u1, u.u2, ediff_fl);
+}
 
 // HMCBase / HMC / ControlHMC (markov_jump_hmc.py:106-148): bit0 = FL accepted, bit1 = flipped,
 // bit2 = the batch-wide R coin fired.
+__device__ __forceinline__ unsigned int decide_discrete_u(double p_flip, double u0, double u1, double ediff,
+                                                          bool coin_fired) {
+    // u0 < leap_prob = min(1, exp(ediff)) (markov_jump_hmc.py:106-114,125).  exp is evaluated only where the
+    // elementary bounds 1 + e <= exp(e) <= 1 / (1 - e)  (e < 0) leave the comparison open; the relative guard
+    // of 2^-40 on both bounds is far wider than the rounding of the three operations, so the outcome is the
+    // one of the exact comparison.  A warp of small |e| skips the ~90-instruction fp64 exp altogether.
+    bool acc = true;                                               // e >= 0: leap_prob = 1 > u0
+    if (!(ediff >= 0.0)) {
+        const double guard = 9.094947017729282e-13;                // 2^-40
+        const double lo = 1.0 + ediff;
+        if (!(u0 < lo - guard * fabs(lo))) {
+            const double hi = __drcp_rn(1.0 - ediff);
+            acc = (u0 > hi + guard * hi) ? false : (u0 < exp(ediff));
+        }
+    }
+    return (acc ? 1u : 0u) | (u1 < p_flip ? 2u : 0u) | (coin_fired ? 4u : 0u);
+}
 MJ_COLD Decision decide_discrete(const LaunchParams& p, long long i, unsigned long long attempt,
                                  double ediff, bool coin_fired) {
     Decision dc; dc.dwell = 0.0; dc.fail = false;
-    const double p_acc = ediff < 0.0 ? exp(ediff) : 1.0;           // leap_prob
     const Uniform3 u = draw_uniforms(p, i, attempt, false);
-    dc.choice = (u.u0 < p_acc ? 1u : 0u) | (u.u1 < p.p_flip ? 2u : 0u) | (coin_fired ? 4u : 0u);
+    dc.choice = decide_discrete_u(p.p_flip, u.u0, u.u1, ediff, coin_fired);
     return dc;
+}
+
+// Streaming-kernel forms.  The exponential draws are (1/rate) * w with w = -log(1 - u) (exp_draw above): w
+// depends on the uniforms only, so the kernel evaluates the three logs BEFORE the trajectory / the energy
+// reduction (draw_log_uniforms) and only the rate-dependent half stays on the critical path.  Same operations,
+// same operands, same results as decide_mj_u / decide_ct_u.
+struct LogUniform3 { double w0, w1, w2; };
+static __device__ __noinline__ LogUniform3 neg_log1m3(double u0, double u1, double u2, bool need_u2) {
+    LogUniform3 w;
+    w.w0 = -log(1.0 - u0);
+    w.w1 = -log(1.0 - u1);
+    w.w2 = need_u2 ? -log(1.0 - u2) : 0.0;
+    return w;
+}
+__device__ __forceinline__ double exp_draw_w(double rate, double w) { return rate == 0.0 ? INFINITY : (1.0 / rate) * w; }
+
+static __device__ __noinline__ Decision decide_mj_w(double p_r, double w0, double w1, double w2,
+                                                    double ediff_l, double ediff_flf) {
+    Decision dc; dc.choice = 0; dc.dwell = 0.0; dc.fail = false;
+    const double rl = jump_rate(ediff_l);
+    const double rflf = jump_rate(ediff_flf);
+    if (!(isfinite(rl) && isfinite(rflf))) { dc.fail = true; return dc; }
+    const double rf = rflf - (rl < rflf ? rl : rflf);              // :368
+    const double tl = exp_draw_w(rl, w0);
+    const double tf = exp_draw_w(rf, w1);
+    const double tr = exp_draw_w(p_r, w2);
+    dc.dwell = tl;
+    if (tf < dc.dwell) { dc.choice = 1; dc.dwell = tf; }
+    if (tr < dc.dwell) { dc.choice = 2; dc.dwell = tr; }
+    return dc;
+}
+static __device__ __noinline__ Decision decide_ct_w(double p_r, double w0, double w1, double w2, double ediff_fl) {
+    Decision dc; dc.choice = 0; dc.dwell = 0.0; dc.fail = false;
+    const double rfl = jump_rate(ediff_fl);
+    if (!isfinite(rfl)) { dc.fail = true; return dc; }
+    const double tfl = exp_draw_w(rfl, w0);
+    const double tf = exp_draw_w(1.0, w1);
+    const double tr = exp_draw_w(p_r, w2);
+    dc.dwell = tf;
+    if (tfl < dc.dwell) { dc.choice = 1; dc.dwell = tfl; }
+    if (tr < dc.dwell) { dc.choice = 2; dc.dwell = tr; }
+    return dc;
+}
+static __device__ __noinline__ unsigned int decide_discrete_s(double p_flip, double u0, double u1, double ediff,
+                                                              bool coin_fired) {
+    return decide_discrete_u(p_flip, u0, u1, ediff, coin_fired);
 }
 
 __device__ __forceinline__ void report_failure(const LaunchParams& p, int it) {

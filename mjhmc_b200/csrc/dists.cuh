@@ -68,6 +68,9 @@ struct TestGaussianD {
     int d;
     __device__ __forceinline__ explicit TestGaussianD(const LaunchParams& p)
         : inv_s2((T)(1.0 / (p.dp[0] * p.dp[0]))), inv_2s2((T)(1.0 / (2.0 * p.dp[0] * p.dp[0]))), d(p.d) {}
+    // dims k0 .. k0+nd-1 of the particle (streaming kernel: several threads share one particle)
+    __device__ __forceinline__ TestGaussianD(const LaunchParams& p, int k0, int nd)
+        : inv_s2((T)(1.0 / (p.dp[0] * p.dp[0]))), inv_2s2((T)(1.0 / (2.0 * p.dp[0] * p.dp[0]))), d(nd) {}
     __device__ __forceinline__ void grad(const T (&x)[D], T (&g)[D]) const {
 #pragma unroll
         for (int k = 0; k < D; ++k) g[k] = x[k] * inv_s2;
@@ -88,6 +91,10 @@ struct DiagGaussianD {
 #pragma unroll
         for (int k = 0; k < D; ++k) j[k] = (k < p.d) ? ((const T*)p.a0)[k] : (T)0;
     }
+    __device__ __forceinline__ DiagGaussianD(const LaunchParams& p, int k0, int nd) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) j[k] = (k < nd) ? ((const T*)p.a0)[k0 + k] : (T)0;
+    }
     __device__ __forceinline__ void grad(const T (&x)[D], T (&g)[D]) const {
 #pragma unroll
         for (int k = 0; k < D; ++k) g[k] = j[k] * x[k];
@@ -103,6 +110,7 @@ struct DiagGaussianD {
 template <typename T, int D>
 struct RoughWellD {
     static constexpr int kind = MJHMC_DIST_ROUGH_WELL;
+    static constexpr bool kLinear = false;       // stream_separable.cuh: no folded-kick form
     static constexpr int kNC = sizeof(T) == 8 ? kSinCoefF64 : kSinCoefF32;
     T inv_s1sq, inv_2s1sq, c_pi;      // c_pi = 2 / scale2 (argument of sin / cos in half-turns)
     T sc[kNC];                        // Q coefficients times -2 pi / scale2
@@ -110,6 +118,12 @@ struct RoughWellD {
     __device__ __forceinline__ explicit RoughWellD(const LaunchParams& p)
         : inv_s1sq((T)(1.0 / (p.dp[0] * p.dp[0]))), inv_2s1sq((T)(1.0 / (2.0 * p.dp[0] * p.dp[0]))),
           c_pi((T)(2.0 / p.dp[1])), d(p.d) {
+#pragma unroll
+        for (int j = 0; j < kNC; ++j) sc[j] = (T)p.coef[j];
+    }
+    __device__ __forceinline__ RoughWellD(const LaunchParams& p, int k0, int nd)
+        : inv_s1sq((T)(1.0 / (p.dp[0] * p.dp[0]))), inv_2s1sq((T)(1.0 / (2.0 * p.dp[0] * p.dp[0]))),
+          c_pi((T)(2.0 / p.dp[1])), d(nd) {
 #pragma unroll
         for (int j = 0; j < kNC; ++j) sc[j] = (T)p.coef[j];
     }

@@ -37,7 +37,7 @@ INFINITE_RATE_MSG = ("Infinite rate. This occurs when calculating transition rat
                      "Try decreasing the leapfrog stepsize/number of steps or dividing "
                      " the energy by a large constant.")
 
-_B200_KWARGS = ("dtype", "seed", "device", "injected_draws", "particle_offset", "V")
+_B200_KWARGS = ("dtype", "seed", "device", "injected_draws", "particle_offset", "V", "kernel")
 
 
 class _CallableEnergy(Distribution):
@@ -97,6 +97,15 @@ class _Engine(object):
             if desc is not None:
                 self.desc, self._desc_keep = desc
                 self.fused = bool(self.lib.mjhmc_fused_supported(C.byref(self.desc)))
+            # kernel="stream": force the TMA-ring streaming kernel (separable energies); default: the library
+            # picks (register kernel for ndims <= 16, streaming kernel above, dense kernels for J / W)
+            self.kernel = opts.get("kernel") or "auto"
+            if self.kernel not in ("auto", "stream"):
+                raise ValueError("kernel must be 'auto' or 'stream'")
+            if self.kernel == "stream":
+                if desc is None or not self.lib.mjhmc_stream_supported(C.byref(self.desc)):
+                    raise ValueError("kernel='stream' needs a separable built-in energy with ndims <= 128")
+                self.fused = True
             mk = lambda a: _device.to_device(a, self.dtype, self.device)
             self.X = [mk(X0), torch.empty((self.d, self.n), dtype=self.tdtype, device=self.device)]
             self.V = [mk(V0), torch.empty((self.d, self.n), dtype=self.tdtype, device=self.device)]
@@ -114,6 +123,7 @@ class _Engine(object):
                 self.EX = self._callback(self.X[0], False, count=False).reshape(-1)
                 self.EV = self._kinetic(self.V[0])
         self.launches = 0
+        self.kernel_events = None
 
     # ---------------------------------------------------------------- helpers
     def ctx(self):
@@ -197,9 +207,15 @@ class _Engine(object):
                     raise IndexError("injected draws exhausted")
                 src, dst = self._state(self.cur), self._state(self.cur ^ 1)
                 o = self._outputs(samples, it0, dwell, choice)
-                _lib.check(self.lib.mjhmc_sample_fused(C.byref(self.desc), C.byref(hp), C.byref(rng), C.byref(src),
-                                                       C.byref(dst), int(n_iter), C.byref(o), self._stream()),
-                           "sample_fused")
+                entry = self.lib.mjhmc_sample_stream if self.kernel == "stream" else self.lib.mjhmc_sample_fused
+                if self.kernel_events is not None:      # bench.py: CUDA events right around the sampler kernel
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record()
+                _lib.check(entry(C.byref(self.desc), C.byref(hp), C.byref(rng), C.byref(src),
+                                 C.byref(dst), int(n_iter), C.byref(o), self._stream()), "sample_fused")
+                if self.kernel_events is not None:
+                    ev[1].record()
+                    self.kernel_events.append(ev)
                 self.launches += 1
                 return self._read_counters()
             return self._launch_unfused(attempt0, n_iter, samples, it0, dwell, choice)

@@ -43,8 +43,12 @@ def test_host_only_entry_points():
     assert lib.mjhmc_fused_supported(ctypes.byref(d)) == 1
     d.ndims = 16
     assert lib.mjhmc_fused_supported(ctypes.byref(d)) == 1
-    d.ndims = 17
-    assert lib.mjhmc_fused_supported(ctypes.byref(d)) == 0
+    d.ndims = 17                                    # above the register kernel: the streaming kernel (<= 128 dims)
+    assert lib.mjhmc_fused_supported(ctypes.byref(d)) == 1 and lib.mjhmc_stream_supported(ctypes.byref(d)) == 1
+    d.ndims = 129
+    assert lib.mjhmc_fused_supported(ctypes.byref(d)) == 0 and lib.mjhmc_stream_supported(ctypes.byref(d)) == 0
+    d.kind, d.ndims = _lib.DIST_FUNNEL, 20          # not separable: no streaming kernel
+    assert lib.mjhmc_fused_supported(ctypes.byref(d)) == 0 and lib.mjhmc_stream_supported(ctypes.byref(d)) == 0
     d.kind = 99
     assert lib.mjhmc_fused_supported(ctypes.byref(d)) == 0
     assert b"bad distribution kind" in lib.mjhmc_last_error()
