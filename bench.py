@@ -77,6 +77,12 @@ WORKLOADS = {
     "gauss16d_control_L1_f32_stream": dict(dist="DiagGaussian", ndims=16, n=8_000_000, sampler="ControlHMC", dtype="float32",
                                            kernel="stream", epsilon=0.5, beta=0.1, L=1, iters=1,
                                            source="HBM roofline point, fp32 states, streaming kernel"),
+    "roughwell2d_mjhmc_stream": dict(dist="RoughWell", ndims=2, n=1_000_000, sampler="MarkovJumpHMC", kernel="stream",
+                                     epsilon=3.0, beta=0.012314380146563053, L=25, iters=64,
+                                     source="search/MJHMC_rw/params.json; streaming kernel"),
+    "roughwell2d_control_stream": dict(dist="RoughWell", ndims=2, n=1_000_000, sampler="ControlHMC", kernel="stream",
+                                       epsilon=0.6687788963317871, beta=0.5385961532592773, L=22, iters=64,
+                                       source="search/control_rw/params_new.json; streaming kernel"),
     # configs[2] as the reference builds it: Gaussian(ndims=100) is DIAGONAL (distributions.py:257-263)
     "gauss100d_diag_mjhmc": dict(dist="DiagGaussian", log_cond=6, ndims=100, n=1_000_000, sampler="MarkovJumpHMC",
                                  epsilon=1.4581446647644043, beta=0.009999999776482582, L=25, iters=1,
@@ -405,14 +411,28 @@ def run_b200(args, w):
                         "algorithmic_flops_per_leapfrog_step": fl, "launch_ms": launch_ms,
                         "hbm_gbs": achieved, "note": "ncu sm__pipe_tensor_cycles_active in profiles/r1_dense_*.txt"}
         else:
+            streaming = w.get("kernel") == "stream" or w["ndims"] > 16
+            if w["L"] <= 4:
+                note = "HBM-bound point"
+            elif streaming:
+                note = ("L=%d leapfrog steps per sample through the streaming kernel: neither HBM- nor fp64-bound yet "
+                        "(DESIGN.md 3.1b)" % w["L"])
+            else:
+                note = ("L=%d leapfrog steps per sample: the kernel is FP64-issue bound "
+                        "(ncu sm__pipe_fp64_cycles_active 71%%, DESIGN.md 3.1), not HBM bound" % w["L"])
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": TRAFFIC.get(args.workload), "peak_source": peak_src,
-                        "kernel": "stream_sample_kernel" if (w.get("kernel") == "stream" or w["ndims"] > 16)
-                                  else "fused_sample_kernel",
-                        "algorithmic_bytes_per_launch": alg, "launch_ms": launch_ms,
-                        "note": ("L=%d leapfrog steps per sample: the kernel is FP64-issue bound "
-                                 "(ncu sm__pipe_fp64_cycles_active 71%%, DESIGN.md 3.1), not HBM bound" % w["L"])
-                        if w["L"] > 4 else "HBM-bound point"}
+                        "kernel": "stream_sample_kernel" if streaming else "fused_sample_kernel",
+                        "algorithmic_bytes_per_launch": alg, "launch_ms": launch_ms, "note": note}
+            if w["dist"] == "RoughWell" and not streaming:
+                # the pipe that does bound this kernel: fp64 instructions of the leapfrog loop per particle-dimension-step
+                # (2 FMAs for kick and drift, 1 merged half kick, 14 for x/s1^2 - c sin(2 pi x / s2): DESIGN.md 3.1)
+                fp64_inst = 17.0 * w["ndims"] * grads_all / world / (ms_max * 1e-3)
+                fp64_peak = 148 * 64 * (clk["sm_mhz"] or 1965.0) * 1e6 if clk else 148 * 64 * 1.965e9
+                roofline["fp64_pipe"] = {"achieved_inst_per_s": fp64_inst, "peak_inst_per_s": fp64_peak,
+                                         "frac": fp64_inst / fp64_peak,
+                                         "note": "algorithmic fp64 instructions of the leapfrog loop only; 64 fp64 lanes per SM "
+                                                 "and clock at the sampled SM clock; ncu sm__pipe_fp64_cycles_active = 71%"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,

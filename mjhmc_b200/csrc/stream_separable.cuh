@@ -45,7 +45,11 @@ __host__ __device__ constexpr int stream_min_blocks() {
     // 1.6x slower than the 1-CTA build; at 2 dims per thread 4 CTAs with a few spilled bytes win over 3
     constexpr int bytes = DT * (int)sizeof(T);
     // energies with a folded linear kick keep no gradient registers: one size class more
-    if (LINEAR) return bytes <= 16 ? 4 : (bytes <= 32 ? 3 : (bytes <= 104 ? 2 : 1));
+#ifndef MJ_STREAM_LIN_T3
+#define MJ_STREAM_LIN_T3 32
+#define MJ_STREAM_LIN_T2 104
+#endif
+    if (LINEAR) return bytes <= 16 ? 4 : (bytes <= MJ_STREAM_LIN_T3 ? 3 : (bytes <= MJ_STREAM_LIN_T2 ? 2 : 1));
     return bytes <= 16 ? 4 : (bytes <= 32 ? 3 : (bytes <= 80 ? 2 : 1));
 }
 

@@ -90,9 +90,10 @@ def test_stream_agrees_with_register_kernel(kind, d, dtype):
     fp32 to the share of particles whose operator choices did not flip."""
     hp = dict(epsilon=0.3, beta=0.2, num_leapfrog_steps=5)
     res = []
+    n_it = 6 if dtype == "float64" else 1          # fp32: one iteration, before 1-ulp differences are amplified
     for kernel in ("stream", "auto"):
         s, dist, _ = _pair(kind, "RoughWell", d, 3000, 11, hp, dtype=dtype, kernel=kernel)
-        res.append((s.sample(6), s.state.V.copy(), _counters(s, dist), s.dwelling_times.copy()))
+        res.append((s.sample(n_it), s.state.V.copy(), _counters(s, dist), s.dwelling_times.copy()))
     if dtype == "float64":
         assert helpers.rel_err(res[0][0], res[1][0]) < 1e-10
         assert helpers.rel_err(res[0][1], res[1][1]) < 1e-10
@@ -102,7 +103,7 @@ def test_stream_agrees_with_register_kernel(kind, d, dtype):
     else:
         X, Xo = res[0][0], res[1][0]
         same = np.all(np.abs(X - Xo) <= 1e-3 * (1 + np.abs(Xo)), axis=0)
-        assert same.mean() > 0.9 and helpers.rel_err(X[:, same], Xo[:, same]) < 1e-4
+        assert same.mean() > 0.97 and helpers.rel_err(X[:, same], Xo[:, same]) < 1e-4
 
 
 def test_stream_one_launch_equals_many():
