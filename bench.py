@@ -93,6 +93,10 @@ WORKLOADS = {
     "gauss100d_diag_control_L1": dict(dist="DiagGaussian", log_cond=6, ndims=100, n=1_000_000, sampler="ControlHMC",
                                       epsilon=0.0010000000474974513, beta=0.009999999776482582, L=1, iters=1,
                                       source="search/control_log_gauss/params.json; reference default diagonal J; streaming kernel"),
+    # configs[4]: Funnel 10-d ContinuousTimeHMC with the autocorrelation / ESS statistics reduced across GPUs
+    "funnel10d_cthmc_ess": dict(dist="Funnel", ndims=10, n=1_000_000, sampler="ContinuousTimeHMC",
+                                epsilon=0.1, beta=0.5, L=10, iters=256, ess=dict(n_lags=128),
+                                source="search/MJHMC_funnel/config.json midpoints; ESS from fft_autocor over 256 recorded steps"),
 }
 DEFAULT_WORKLOAD = "roughwell2d_mjhmc"
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full captures (profiles/)
@@ -265,6 +269,47 @@ class ClockSampler(object):
         return out
 
 
+def _oracle_ess_worker(args):
+    w, n, seed = args
+    from oracle import mjhmc_oracle as orc
+    X, V = _init_cloud(w, n, seed)
+    s = orc.OracleSampler(w["sampler"], _oracle_energy(w), X, V=V, epsilon=w["epsilon"], beta=w["beta"],
+                          num_leapfrog_steps=w["L"], draws=orc.FastNumpyDraws(seed), resample=False)
+    t0 = time.perf_counter()
+    S = s.sample(w["iters"], preserve_order=True)                      # (d, n, T)
+    t_sample = time.perf_counter() - t0
+    f = np.fft.fft(S, axis=-1)
+    ac = np.real(np.sum(np.fft.ifft(f * np.conj(f), axis=-1), axis=(0, 1)))   # un-normalised, summed over dims and particles
+    return ac, t_sample, time.perf_counter() - t0
+
+
+def run_reference_ess(w, n_per_core=2000):
+    """ESS/s of the numpy port on all host cores: T recorded steps per chain, fft_autocor over all chains."""
+    import multiprocessing as mp
+    from oracle import mjhmc_oracle as orc
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_oracle_ess_worker, [(w, n_per_core, 300 + r) for r in range(cores)])
+    ac = sum(r[0] for r in res)
+    ac = ac / ac[0]
+    ess = _ess_from_curve(ac[:w["ess"]["n_lags"]], len(ac))
+    t = max(r[2] for r in res)
+    n = n_per_core * cores
+    return dict(ess_per_chain=ess, chains=n, seconds=t, ess_per_s=ess * n / t, cores=cores, kind="port",
+                sample="%d chains (%d per core x %d cores), %d recorded steps each" % (n, n_per_core, cores, w["iters"]))
+
+
+def _ess_from_curve(ac, T):
+    """ESS = T / (1 + 2 sum_{tau>=1}^{first rho<0} rho_tau) on the first len(ac) lags of the fft_autocor curve."""
+    s = 0.0
+    for tau in range(1, len(ac)):
+        if ac[tau] < 0:
+            break
+        s += ac[tau]
+    return T / (1.0 + 2.0 * s)
+
+
 def make_sampler(w, rank, dtype=None, seed=2024):
     dtype = dtype or w.get("dtype", DTYPE)
     from mjhmc_b200.misc import distributions as D
@@ -359,15 +404,48 @@ def run_b200(args, w):
     grads_all, launches_all, grads_ref_all = int(gg[0].item()), int(gg[1].item()), int(gg[2].item())
     value = grads_all / (ms_max * 1e-3)
 
+    # ---- ESS/s (BASELINE metric iii): T recorded steps, per-GPU autocorrelation sums, one all-reduce of float64[n_lags]
+    ess = None
+    if w.get("ess"):
+        from mjhmc_b200 import parallel
+        n_lags = w["ess"]["n_lags"]
+        barrier()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        S = sampler.sample_device(iters)
+        e1.record()
+        part = parallel.autocorr_partial(S, n_lags=n_lags, circular=True)
+        if world > 1:
+            dist_pkg.all_reduce(part)                                   # the statistics "gathered over NVLink"
+        e2.record()
+        barrier()
+        ac = part.double().cpu().numpy()
+        ac = ac / ac[0]
+        ts = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist_pkg.all_reduce(ts, op=dist_pkg.ReduceOp.MAX)
+        ess_chain = _ess_from_curve(ac, iters)
+        total_s = float(ts.sum().item()) * 1e-3
+        ess = {"definition": "T / (1 + 2 sum_{tau>=1}^{first rho<0} rho_tau) on the circular fft_autocor curve (autocor.py:37-49), "
+                             "first %d lags" % n_lags,
+               "T": iters, "n_lags": n_lags, "chains": w["n"] * world, "ess_per_chain": ess_chain,
+               "sampling_ms": float(ts[0].item()), "autocorr_allreduce_ms": float(ts[1].item()),
+               "ess_per_s": ess_chain * w["n"] * world / total_s, "rho_1": float(ac[1]), "rho_last": float(ac[-1])}
+        del S, part
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            ess["cpu"] = run_reference_ess(w)
+
     # ---- e2e: host buffers in, host samples out, through the public API, every step
     from mjhmc_b200.samplers.hmc_state import HMCState
     Xh = torch.as_tensor(X0).pin_memory()                  # host inputs live in pinned memory
     Vh = torch.as_tensor(V0).pin_memory()
     e2e_steps = max(1, min(args.steps, 5))
 
+    e2e_iters = 8 if w.get("ess") else iters                 # the ESS workload records 256 steps on the device only
+
     def e2e_step():
         sampler.state = HMCState.from_buffers(sampler, Xh, Vh)   # H2D from pinned memory at the next launch
-        return sampler.sample(iters)                         # D2H of (ndims, iters * n)
+        return sampler.sample(e2e_iters)                     # D2H of (ndims, iters * n)
 
     for _ in range(2):                                       # warm the pinned staging buffers (not timed)
         res = e2e_step()
@@ -426,8 +504,8 @@ def run_b200(args, w):
                         "algorithmic_bytes_per_launch": alg, "launch_ms": launch_ms, "note": note}
             if w["dist"] == "RoughWell" and not streaming:
                 # the pipe that does bound this kernel: fp64 instructions of the leapfrog loop per particle-dimension-step
-                # (2 FMAs for kick and drift, 1 merged half kick, 14 for x/s1^2 - c sin(2 pi x / s2): DESIGN.md 3.1)
-                fp64_inst = 17.0 * w["ndims"] * grads_all / world / (ms_max * 1e-3)
+                # (3 FMAs for the two half kicks and the drift, 15 for x/s1^2 - c sin(2 pi x / s2): dists.cuh)
+                fp64_inst = 18.0 * w["ndims"] * grads_all / world / (ms_max * 1e-3)
                 fp64_peak = 148 * 64 * (clk["sm_mhz"] or 1965.0) * 1e6 if clk else 148 * 64 * 1.965e9
                 roofline["fp64_pipe"] = {"achieved_inst_per_s": fp64_inst, "peak_inst_per_s": fp64_peak,
                                          "frac": fp64_inst / fp64_peak,
@@ -447,8 +525,9 @@ def run_b200(args, w):
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps, "iterations_per_step": e2e_iters},
             "gpu_launches": launches_all,
+            "ess": ess,
             "clocks": clk,
             "wall_s_timed_region": t_wall,
             "grad_evals_executed": grads_all,

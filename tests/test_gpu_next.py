@@ -110,3 +110,19 @@ def test_fair_initialisation_cache(tmp_path, monkeypatch):
     d3 = helpers.pin_init(D.TestGaussian(ndims=2, nbatch=30), np.random.RandomState(1).randn(2, 30))
     s3 = ControlHMC(distribution=d3, epsilon=0.6, beta=0.3, num_leapfrog_steps=3, seed=9, V=np.zeros((2, 30)))
     np.testing.assert_allclose(var, np.var(s3.sample(50), ddof=1), rtol=1e-12)
+
+
+def test_autocorrelation_kernels_match_the_reference_functions():
+    """The device kernels behind fft_autocor / slow_autocorrelation against outputs of the reference's own
+    functions (tests/golden/autocor_reference.npz, generate_autocor_golden.py)."""
+    import os
+    from mjhmc_b200.misc import autocor
+    g = np.load(os.path.join(helpers.GOLDEN, "autocor_reference.npz"))
+    for tag in "abc":
+        x = g["x_" + tag]
+        np.testing.assert_allclose(autocor.fft_autocor(x), g["fft_" + tag], rtol=1e-10, atol=1e-12)
+        e = np.arange(x.shape[2], dtype=np.float64)
+        slow, _, _ = autocor.slow_autocorrelation(x, e, e, half_window=False)
+        np.testing.assert_allclose(slow, g["slow_" + tag], rtol=1e-10, atol=1e-12)
+        ac, _, _ = autocor.autocorrelation(x, e, e, half_window=False, brute_force=False)
+        np.testing.assert_allclose(ac, g["fft_" + tag], rtol=1e-10, atol=1e-12)

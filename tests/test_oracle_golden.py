@@ -163,3 +163,16 @@ def test_fft_autocor_is_circular_mean_product():
     brute = np.array([np.mean(s * np.roll(s, -t, axis=-1)) for t in range(16)])
     np.testing.assert_allclose(ac, brute / brute[0], atol=1e-12)
     assert orc.ess_from_autocor(np.array([1.0, 0.5, 0.25, -0.1, 0.3])) == 5 / (1 + 2 * 0.75)
+
+
+def test_oracle_fft_autocor_matches_the_reference_function():
+    """autocor_reference.npz: outputs of the reference's own fft_autocor / slow_autocorrelation source
+    (tests/golden/generate_autocor_golden.py), numpy.fft standing in for mklfft."""
+    import os
+    g = np.load(os.path.join(helpers.GOLDEN, "autocor_reference.npz"))
+    for tag in "abc":
+        x = g["x_" + tag]
+        np.testing.assert_allclose(orc.fft_autocor(x), g["fft_" + tag], rtol=1e-12, atol=1e-13)
+        T = x.shape[2]
+        slow = np.array([np.mean(x ** 2)] + [np.mean(x[:, :, :-t] * x[:, :, t:]) for t in range(1, T - 1)])
+        np.testing.assert_allclose(slow / slow[0], g["slow_" + tag], rtol=1e-12, atol=1e-13)
