@@ -44,6 +44,26 @@ __device__ __forceinline__ T kinetic(const T (&v)[D]) {
 template <class Dist, typename T, int D>
 __device__ __forceinline__ void leapfrog_L(const Dist& dist, T (&x)[D], T (&v)[D], T (&g)[D],
                                            T eps, T neg_half_eps, int L) {
+#ifdef MJ_MERGED_KICKS
+    // the closing half kick of step s and the opening half kick of step s+1 use the same gradient: one full kick
+    // (v - eps g instead of (v - eps/2 g) - eps/2 g: one rounding fewer, one fp64 FMA per dim and step fewer)
+    if (L <= 0) return;
+    const T neg_eps = neg_half_eps + neg_half_eps;
+#pragma unroll
+    for (int k = 0; k < D; ++k) v[k] += neg_half_eps * g[k];
+    for (int s = 1; s < L; ++s) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) x[k] += eps * v[k];
+        dist.grad(x, g);
+#pragma unroll
+        for (int k = 0; k < D; ++k) v[k] += neg_eps * g[k];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) x[k] += eps * v[k];
+    dist.grad(x, g);
+#pragma unroll
+    for (int k = 0; k < D; ++k) v[k] += neg_half_eps * g[k];
+#else
     for (int s = 0; s < L; ++s) {
 #pragma unroll
         for (int k = 0; k < D; ++k) v[k] += neg_half_eps * g[k];
@@ -53,6 +73,7 @@ __device__ __forceinline__ void leapfrog_L(const Dist& dist, T (&x)[D], T (&v)[D
 #pragma unroll
         for (int k = 0; k < D; ++k) v[k] += neg_half_eps * g[k];
     }
+#endif
 }
 
 // FLF cache flags (one byte per particle).  bit0 is the reference's cache_active
