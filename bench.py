@@ -83,6 +83,8 @@ WORKLOADS = {
     "roughwell2d_control_stream": dict(dist="RoughWell", ndims=2, n=1_000_000, sampler="ControlHMC", kernel="stream",
                                        epsilon=0.6687788963317871, beta=0.5385961532592773, L=22, iters=64,
                                        source="search/control_rw/params_new.json; streaming kernel"),
+    "roughwell10d_control_L1_stream": dict(dist="RoughWell", ndims=10, n=8_000_000, sampler="ControlHMC", kernel="stream",
+                                           epsilon=0.5, beta=0.1, L=1, iters=1, source="HBM roofline point, streaming kernel"),
     # configs[2] as the reference builds it: Gaussian(ndims=100) is DIAGONAL (distributions.py:257-263)
     "gauss100d_diag_mjhmc": dict(dist="DiagGaussian", log_cond=6, ndims=100, n=1_000_000, sampler="MarkovJumpHMC",
                                  epsilon=1.4581446647644043, beta=0.009999999776482582, L=25, iters=1,

@@ -179,13 +179,109 @@ __global__ void __launch_bounds__(kAcP * kAcG) autocorr_kernel(const T* __restri
     }
 }
 
+// Register-blocked form: thread (p, g) owns particle p of the tile and kAbR consecutive lags, and keeps a
+// sliding window of the series in registers, so 16 shared-memory loads feed 64 fp64 FMAs (the kernel above
+// issues two loads per FMA and is bound by shared-memory bandwidth at 1/8 of the fp64 rate).  The series tile is
+// extended past T by its own beginning (circular) or by zeros (linear) so the window needs no index arithmetic;
+// a block walks several particle tiles and flushes its per-lag sums once (n_lags atomics per block, not per tile).
+constexpr int kAbP = 16;                 // particles per tile
+constexpr int kAbG = 16;                 // lag groups per block
+constexpr int kAbR = 8;                  // lags per thread and pass
+constexpr int kAbPass = kAbG * kAbR;     // lags per pass of a block
+
+template <typename T>
+__global__ void __launch_bounds__(kAbP * kAbG) autocorr_blocked_kernel(const T* __restrict__ samples, long long stride_k,
+                                                                       long long stride_it, long long n, int Tn, int n_lags,
+                                                                       int circular, double* __restrict__ ac, int ext) {
+    extern __shared__ double smem_ac[];
+    double* tile = smem_ac;                         // [ext][kAbP]
+    double* lag_sum = smem_ac + (size_t)ext * kAbP; // [n_passes * kAbPass]
+    const int p = threadIdx.x % kAbP, g = threadIdx.x / kAbP;
+    const int n_pass = (n_lags + kAbPass - 1) / kAbPass;
+    for (int q = threadIdx.x; q < n_pass * kAbPass; q += blockDim.x) lag_sum[q] = 0.0;
+    const T* base = samples + (long long)blockIdx.y * stride_k;
+    const long long n_tiles = (n + kAbP - 1) / kAbP;
+    for (long long tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+        __syncthreads();                                             // the previous tile is no longer read
+        const long long i = tl * kAbP + p;
+        for (int e = g; e < ext; e += kAbG) {
+            double v = 0.0;
+            if (i < n) {
+                if (e < Tn) v = (double)base[(long long)e * stride_it + i];
+                else if (circular) v = (double)base[(long long)(e % Tn) * stride_it + i];
+            }
+            tile[e * kAbP + p] = v;
+        }
+        __syncthreads();
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const int tau0 = pass * kAbPass + g * kAbR;
+            double acc[kAbR];
+#pragma unroll
+            for (int j = 0; j < kAbR; ++j) acc[j] = 0.0;
+            double b[2 * kAbR];
+#pragma unroll
+            for (int j = 0; j < kAbR; ++j) b[j] = tile[(tau0 + j) * kAbP + p];
+            for (int t = 0; t < Tn; t += kAbR) {
+                double a[kAbR];
+#pragma unroll
+                for (int j = 0; j < kAbR; ++j) {
+                    a[j] = t + j < Tn ? tile[(t + j) * kAbP + p] : 0.0;
+                    b[kAbR + j] = tile[(t + tau0 + kAbR + j) * kAbP + p];
+                }
+#pragma unroll
+                for (int ii = 0; ii < kAbR; ++ii)
+#pragma unroll
+                    for (int j = 0; j < kAbR; ++j) acc[j] = fma(a[ii], b[ii + j], acc[j]);
+#pragma unroll
+                for (int j = 0; j < kAbR; ++j) b[j] = b[kAbR + j];
+            }
+            // sum over the 16 particles of the tile (a half-warp), then one owner per lag
+#pragma unroll
+            for (int j = 0; j < kAbR; ++j) {
+#pragma unroll
+                for (int o = kAbP / 2; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+            }
+            if (p == 0) {
+#pragma unroll
+                for (int j = 0; j < kAbR; ++j) lag_sum[tau0 + j] += acc[j];
+            }
+        }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < n_lags; q += blockDim.x)
+        if (lag_sum[q] != 0.0) atomicAdd(ac + q, lag_sum[q]);
+}
+
 cudaError_t launch_autocorr(int dtype, int d, const void* samples, long long stride_k, long long stride_it,
                             long long n, int Tn, int n_lags, int circular, double* ac, cudaStream_t s) {
     if (n == 0 || Tn == 0 || n_lags == 0) return cudaSuccess;
+    cudaError_t e;
+    // blocked kernel when the extended tile fits
+    const int n_pass = (n_lags + kAbPass - 1) / kAbPass;
+    const int ext = (Tn + kAbR - 1) / kAbR * kAbR + n_pass * kAbPass;
+    const size_t smem_b = sizeof(double) * ((size_t)ext * kAbP + (size_t)n_pass * kAbPass);
+    if (smem_b <= 200 * 1024) {
+        const long long n_tiles = (n + kAbP - 1) / kAbP;
+        long long gx = (148 * 4 + d - 1) / d;
+        if (gx > n_tiles) gx = n_tiles;
+        if (gx < 1) gx = 1;
+        dim3 grid((unsigned)gx, (unsigned)d);
+        if (dtype == MJHMC_F64) {
+            e = cudaFuncSetAttribute(autocorr_blocked_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+            if (e != cudaSuccess) return e;
+            autocorr_blocked_kernel<double><<<grid, kAbP * kAbG, smem_b, s>>>((const double*)samples, stride_k, stride_it, n,
+                                                                               Tn, n_lags, circular, ac, ext);
+        } else {
+            e = cudaFuncSetAttribute(autocorr_blocked_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+            if (e != cudaSuccess) return e;
+            autocorr_blocked_kernel<float><<<grid, kAbP * kAbG, smem_b, s>>>((const float*)samples, stride_k, stride_it, n,
+                                                                              Tn, n_lags, circular, ac, ext);
+        }
+        return cudaGetLastError();
+    }
     const size_t smem = sizeof(double) * (size_t)Tn * kAcP;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     dim3 grid((unsigned)((n + kAcP - 1) / kAcP), (unsigned)d);
-    cudaError_t e;
     if (dtype == MJHMC_F64) {
         e = cudaFuncSetAttribute(autocorr_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -184,6 +184,26 @@ def test_autocorrelation_kernel_matches_fft_autocor():
     np.testing.assert_allclose(ac32, ref[:10], atol=1e-5)
 
 
+@pytest.mark.parametrize("T,n_lags,N", [(300, 300, 37), (129, 200, 16), (50, 7, 1), (1000, 1000, 20), (1500, 1500, 5)])
+def test_autocorrelation_kernels_multi_pass_and_ragged(T, n_lags, N):
+    """The register-blocked kernel over several 128-lag passes, ragged particle tiles, T not a multiple of 8, more
+    lags than steps (circular wrap), and the plain kernel where the extended tile no longer fits in shared memory."""
+    import torch
+    from mjhmc_b200 import parallel
+    rs = np.random.RandomState(T)
+    x = np.cumsum(rs.randn(2, T, N), axis=1) * 0.1 + rs.randn(2, T, N)         # (d, T, N) device layout
+    S = torch.as_tensor(x, device="cuda")
+    circ = parallel.autocorr_partial(S, n_lags=n_lags, circular=True).cpu().numpy()
+    want_c = np.array([np.sum(x * np.roll(x, -(tau % T), axis=1)) for tau in range(n_lags)])
+    np.testing.assert_allclose(circ, want_c, rtol=1e-11, atol=1e-9)
+    lin_lags = min(n_lags, T)
+    lin = parallel.autocorr_partial(S, n_lags=lin_lags, circular=False).cpu().numpy()
+    want_l = np.array([np.sum(x[:, :T - tau] * x[:, tau:]) for tau in range(lin_lags)])
+    np.testing.assert_allclose(lin, want_l, rtol=1e-11, atol=1e-9)
+    c32 = parallel.autocorr_partial(S.float(), n_lags=min(n_lags, 16), circular=True).cpu().numpy()
+    np.testing.assert_allclose(c32, want_c[:min(n_lags, 16)], rtol=1e-5, atol=1e-3)
+
+
 @pytest.mark.parametrize("kind", ["ControlHMC", "MarkovJumpHMC"])
 def test_shard_invariance_single_gpu(kind):
     """T7 on one device: the cloud sampled whole == the two halves sampled separately with
