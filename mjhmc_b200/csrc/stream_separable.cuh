@@ -163,7 +163,7 @@ __device__ __forceinline__ void stream_trajectory(const Dist& dist, T (&x)[DT], 
     e_pot = dist.energy(x);
 }
 
-template <class Dist, typename T, int DT, int SAMPLER>
+template <class Dist, typename T, int DT, int SAMPLER, int LOGG>
 __global__ void __launch_bounds__(kStreamThreads, stream_min_blocks<T, DT, Dist::kLinear>())
 stream_sample_kernel(const __grid_constant__ LaunchParams p, const __grid_constant__ CUtensorMap tmX,
                      const __grid_constant__ CUtensorMap tmV, const StreamCfg cfg) {
@@ -176,7 +176,10 @@ stream_sample_kernel(const __grid_constant__ LaunchParams p, const __grid_consta
     constexpr unsigned kBoxElems = (unsigned)kStreamThreads * DT;
     constexpr unsigned kStageBytes = 2u * kBoxElems * (unsigned)sizeof(T);
 
-    const int d = p.d, G = cfg.G, P = cfg.P, stages = cfg.stages;
+    // warps per 32-particle column block and particles per tile are compile-time: every shared-memory row offset
+    // j * P below is an immediate (with a run-time P the address arithmetic was a quarter of the per-tile code)
+    constexpr int G = 1 << LOGG, P = kStreamThreads / G;
+    const int d = p.d, stages = cfg.stages;
     T* const ring = (T*)smem_raw;
     unsigned char* const fixed = smem_raw + (size_t)stages * kStageBytes;
     int* const coin = (int*)fixed;                                   // [32] batch-wide R coins (discrete samplers)
@@ -187,7 +190,7 @@ stream_sample_kernel(const __grid_constant__ LaunchParams p, const __grid_consta
     T* const red = coef + kStreamWarps * 2 * DT;                     // [kStreamRed][G][P]               (G > 1)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int cb = warp >> cfg.logG, g = warp & (G - 1);
+    const int cb = warp >> LOGG, g = warp & (G - 1);
     const int c = cb * 32 + lane;                  // particle column inside the tile
     const int k0 = g * DT;                         // first dim of this thread
     const int nd = max(0, min(DT, d - k0));        // dims of this thread
@@ -512,8 +515,8 @@ cudaError_t stream_make_maps(const LaunchParams& p, int dtype, int P, int rows, 
                              int* use_tma);
 int stream_sm_count();
 
-template <class Dist, typename T, int DT, int SAMPLER>
-cudaError_t launch_stream_s(const LaunchParams& p, const StreamPlan& pl, int dtype, cudaStream_t stream) {
+template <class Dist, typename T, int DT, int SAMPLER, int LOGG>
+cudaError_t launch_stream_g(const LaunchParams& p, const StreamPlan& pl, int dtype, cudaStream_t stream) {
     StreamCfg cfg;
     cfg.G = pl.G; cfg.logG = pl.logG;
     cfg.P = 32 * kStreamWarps / pl.G;
@@ -541,7 +544,7 @@ cudaError_t launch_stream_s(const LaunchParams& p, const StreamPlan& pl, int dty
     if (!cfg.use_tma) stages = 1;
     cfg.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + fixed;
-    auto kern = stream_sample_kernel<Dist, T, DT, SAMPLER>;
+    auto kern = stream_sample_kernel<Dist, T, DT, SAMPLER, LOGG>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
@@ -553,6 +556,18 @@ cudaError_t launch_stream_s(const LaunchParams& p, const StreamPlan& pl, int dty
     stream_note_launch(cfg.use_tma, stages, grid, per_sm, pl.G, DT, smem);
     kern<<<(unsigned)grid, kStreamThreads, smem, stream>>>(p, mx, mv, cfg);
     return cudaGetLastError();
+}
+
+// several warps per particle only exist for ndims > 16, i.e. at 10, 13 or 16 dims per thread (stream_plan)
+template <class Dist, typename T, int DT, int SAMPLER>
+cudaError_t launch_stream_s(const LaunchParams& p, const StreamPlan& pl, int dtype, cudaStream_t stream) {
+    if (pl.logG == 0) return launch_stream_g<Dist, T, DT, SAMPLER, 0>(p, pl, dtype, stream);
+    if constexpr (DT >= 10) {
+        if (pl.logG == 1) return launch_stream_g<Dist, T, DT, SAMPLER, 1>(p, pl, dtype, stream);
+        if (pl.logG == 2) return launch_stream_g<Dist, T, DT, SAMPLER, 2>(p, pl, dtype, stream);
+        if (pl.logG == 3) return launch_stream_g<Dist, T, DT, SAMPLER, 3>(p, pl, dtype, stream);
+    }
+    return cudaErrorInvalidConfiguration;
 }
 
 template <class Dist, typename T, int DT>
