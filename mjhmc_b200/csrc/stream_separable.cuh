@@ -39,17 +39,14 @@ struct StreamCfg {
 // Resident CTAs per SM the register allocator must allow: the live arrays are the proposal (x, v, g) of DT dims;
 // everything else (Philox, exp, log) is out of line.  More CTAs = more warps to hide the dependent-issue latency of
 // the per-particle chains; the TMA ring keeps the loads in flight whatever the register budget is.
-template <typename T, int DT, bool LINEAR>
+template <typename T, int DT, bool LINEAR, bool MJ = false>
 __host__ __device__ constexpr int stream_min_blocks() {
-    // measured on B200 (profiles/r1_stream_*.txt): a spilling 2-CTA build of the 13-dims-per-thread kernel is
-    // 1.6x slower than the 1-CTA build; at 2 dims per thread 4 CTAs with a few spilled bytes win over 3
+    // measured on B200 (profiles/r1_stream_*.txt): at 2 dims per thread 4 CTAs with a few spilled
+    // bytes win over 3; energies with a folded linear kick keep no gradient registers and go one size class
+    // further; the MarkovJumpHMC body (FLF cache, three holding times) spills at 13 fp64 dims per thread under the
+    // 128-register cap of two CTAs and is 8 % faster as one CTA with a 4-stage ring.
     constexpr int bytes = DT * (int)sizeof(T);
-    // energies with a folded linear kick keep no gradient registers: one size class more
-#ifndef MJ_STREAM_LIN_T3
-#define MJ_STREAM_LIN_T3 32
-#define MJ_STREAM_LIN_T2 104
-#endif
-    if (LINEAR) return bytes <= 16 ? 4 : (bytes <= MJ_STREAM_LIN_T3 ? 3 : (bytes <= MJ_STREAM_LIN_T2 ? 2 : 1));
+    if (LINEAR) return bytes <= 16 ? 4 : (bytes <= 32 ? 3 : (bytes <= (MJ ? 103 : 104) ? 2 : 1));
     return bytes <= 16 ? 4 : (bytes <= 32 ? 3 : (bytes <= 80 ? 2 : 1));
 }
 
@@ -164,7 +161,7 @@ __device__ __forceinline__ void stream_trajectory(const Dist& dist, T (&x)[DT], 
 }
 
 template <class Dist, typename T, int DT, int SAMPLER, int LOGG>
-__global__ void __launch_bounds__(kStreamThreads, stream_min_blocks<T, DT, Dist::kLinear>())
+__global__ void __launch_bounds__(kStreamThreads, stream_min_blocks<T, DT, Dist::kLinear, SAMPLER == MJHMC_SAMPLER_MARKOV_JUMP>())
 stream_sample_kernel(const __grid_constant__ LaunchParams p, const __grid_constant__ CUtensorMap tmX,
                      const __grid_constant__ CUtensorMap tmV, const StreamCfg cfg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];   // TMA without swizzle: 128-byte aligned boxes
@@ -530,7 +527,7 @@ cudaError_t launch_stream_g(const LaunchParams& p, const StreamPlan& pl, int dty
                          (size_t)kStreamWarps * 2 * DT * sizeof(T) +
                          (pl.G > 1 ? (size_t)kStreamRed * kStreamThreads * sizeof(T) : 0);
     // as many CTAs per SM as the registers allow, but at least two ring stages each
-    int nb = stream_min_blocks<T, DT, Dist::kLinear>(), stages = 0;
+    int nb = stream_min_blocks<T, DT, Dist::kLinear, SAMPLER == MJHMC_SAMPLER_MARKOV_JUMP>(), stages = 0;
     for (; nb >= 1; --nb) {
         // 228 KB of shared memory per SM, 1 KB of it reserved per resident CTA (probed on B200 with
         // mjhmc_stream_probe_blocks: 115712 dynamic bytes is the most two CTAs can have each); 512 bytes of slack
