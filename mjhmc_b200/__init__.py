@@ -11,7 +11,8 @@ __version__ = "0.1.0"
 
 
 def install_alias(name="mjhmc"):
-    from . import misc, samplers
+    from . import misc, samplers, search
+    from .search import objective
     from .misc import autocor, distributions, gen_mj_init, utils
     from .samplers import hmc_state, markov_jump_hmc
     pkg = sys.modules[__name__]
@@ -23,6 +24,8 @@ def install_alias(name="mjhmc"):
     sys.modules[name + ".misc.autocor"] = autocor
     sys.modules[name + ".misc.gen_mj_init"] = gen_mj_init
     sys.modules[name + ".samplers"] = samplers
+    sys.modules[name + ".search"] = search
+    sys.modules[name + ".search.objective"] = objective
     sys.modules[name + ".samplers.markov_jump_hmc"] = markov_jump_hmc
     sys.modules[name + ".samplers.hmc_state"] = hmc_state
     return pkg

@@ -255,3 +255,25 @@ def test_install_alias(fake_engine):
         for k in [k for k in sys.modules if k == "mjhmc" or k.startswith("mjhmc.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_every_bench_workload_has_a_cpu_arm():
+    """bench.py --impl reference / cpu_baseline: the oracle energy, the synthetic cloud and one sampling iteration of
+    every workload (tiny particle count), so a new workload cannot ship without its CPU arm."""
+    import bench
+    from oracle import mjhmc_oracle as orc
+    for name, w in bench.WORKLOADS.items():
+        X, V = bench._init_cloud(w, 6, 0)
+        assert X.shape == V.shape == (w["ndims"], 6), name
+        s = orc.OracleSampler(w["sampler"], bench._oracle_energy(w), X, V=V, epsilon=w["epsilon"], beta=w["beta"],
+                              num_leapfrog_steps=min(w["L"], 2), draws=orc.FastNumpyDraws(1), resample=False)
+        s.sampling_iteration()
+        assert np.all(np.isfinite(s.X)), name
+        assert bench.algorithmic_bytes_per_launch(w) > 0
+
+
+def test_ess_definition():
+    import bench
+    ac = np.array([1.0, 0.5, 0.25, -0.1, 0.3])
+    assert abs(bench._ess_from_curve(ac, 100) - 100 / (1 + 2 * 0.75)) < 1e-12
+    assert bench._ess_from_curve(np.array([1.0, -0.2]), 10) == 10.0
