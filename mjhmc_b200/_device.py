@@ -47,4 +47,7 @@ def to_device(a, dtype, device):
     """numpy / torch array -> contiguous device tensor of `dtype` (a copy unless already right)."""
     if isinstance(a, torch.Tensor):
         return a.to(device=device, dtype=torch_dtype(dtype)).contiguous()
-    return torch.as_tensor(np.ascontiguousarray(a), device=device).to(torch_dtype(dtype)).contiguous()
+    arr = np.ascontiguousarray(a)
+    if not arr.flags.writeable:          # e.g. arrays out of np.load: torch refuses read-only memory
+        arr = arr.copy()
+    return torch.as_tensor(arr, device=device).to(torch_dtype(dtype)).contiguous()

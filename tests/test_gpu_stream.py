@@ -165,3 +165,39 @@ def test_reference_default_gaussian_100d_runs_on_the_streaming_kernel():
     X, Xo = s.sample(3), o.sample(3)
     assert helpers.rel_err(X, Xo) < 1e-10
     assert _counters(s, dist) == [o.counters()[k] for k in KEYS]
+
+
+@pytest.mark.parametrize("d", [20, 40, 100])
+@pytest.mark.parametrize("kind", ["MarkovJumpHMC", "ControlHMC"])
+def test_stream_kernel_fp32_with_several_threads_per_particle(kind, d):
+    """fp32 states, G > 1: one iteration from the same state against the fp64 oracle (tolerance 1e-4 on the particles
+    whose operator choice did not flip in single precision)."""
+    dist_name = "Gaussian" if d != 40 else "RoughWell"
+    hp = dict(epsilon=0.2, beta=0.3, num_leapfrog_steps=3)
+    s, dist, o = _pair(kind, dist_name, d, 1500, 40 + d, hp, dtype="float32")
+    X, Xo = s.sample(1), o.sample(1)
+    same = np.all(np.abs(X - Xo) <= 1e-3 * (1 + np.abs(Xo)), axis=0)
+    assert same.mean() > 0.97 and helpers.rel_err(X[:, same], Xo[:, same]) < 1e-4
+
+
+@pytest.mark.parametrize("d", [6, 24, 100])
+def test_stream_kernel_backoff_with_several_threads_per_particle(d):
+    """A non-finite rate inside a multi-iteration launch when the particle is spread over G warps: the failed
+    particle must keep its state, the launch must be replayed and the batch-wide back-off of
+    markov_jump_hmc.py:376-389 must give the oracle's trajectory and counters."""
+    from mjhmc_b200.misc.distributions import TestGaussian
+    from mjhmc_b200.samplers.markov_jump_hmc import MarkovJumpHMC
+    rs = np.random.RandomState(d)
+    N = 70
+    X0, V0 = rs.randn(d, N) * 0.3, rs.randn(d, N) * 0.1
+    X0[:, 3] = 40.0                                     # H - H_L = 0.094 d x^2 > 709.78 at eps = 1, L = 1: exp() overflows
+    dist = helpers.pin_init(TestGaussian(ndims=d, nbatch=N), X0)
+    hp = dict(epsilon=1.0, beta=0.5, num_leapfrog_steps=1)
+    s = MarkovJumpHMC(distribution=dist, V=V0, seed=21, resample=False, kernel="stream", **hp)
+    o = orc.OracleSampler("MarkovJumpHMC", orc.TestGaussianEnergy(1.0), X0, V=V0, draws=orc.PhiloxDraws(21),
+                          resample=False, **hp)
+    X, Xo = s.sample(3), o.sample(3)
+    assert helpers.rel_err(X, Xo) < 1e-10
+    assert _counters(s, dist) == [o.counters()[k] for k in KEYS]
+    assert s.epsilon == o.epsilon and s.num_leapfrog_steps == o.num_leapfrog_steps
+    assert o.counters()["dEdX"] > N + 3 * 2 * N        # more than three plain iterations: the back-off ran
