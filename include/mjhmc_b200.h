@@ -42,7 +42,8 @@ enum {
     MJHMC_DIST_FUNNEL_LITERAL = 4, /* tf_distributions.py:158-165 as written        p[0]=scale        */
     MJHMC_DIST_DENSE_GAUSSIAN = 5, /* distributions.py:268-273 full J; a0 = (J+J^T)/2 [ndims x ndims];
                                       fp32 only: a1 = workspace filled by mjhmc_dense_tf32_prepare */
-    MJHMC_DIST_PRODUCT_OF_T   = 6  /* distributions.py:420-433; a0=W [ndims x nbasis], a1=nu, a2=b    */
+    MJHMC_DIST_PRODUCT_OF_T   = 6, /* distributions.py:420-433; a0=W [ndims x nbasis], a1=nu, a2=b    */
+    MJHMC_DIST_MULTIMODAL     = 7  /* distributions.py:314-335  two Gaussians at -/+ 2*separation along dim 0; p[0]=separation */
 };
 
 /* sampler classes (samplers/markov_jump_hmc.py) */

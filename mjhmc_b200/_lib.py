@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("MJHMC_B200_LIB") or os.path.join(HERE, "libmjhmc_b200
 
 F32, F64 = 0, 1
 DIST_TEST_GAUSSIAN, DIST_DIAG_GAUSSIAN, DIST_ROUGH_WELL, DIST_FUNNEL, DIST_FUNNEL_LITERAL, \
-    DIST_DENSE_GAUSSIAN, DIST_PRODUCT_OF_T = range(7)
+    DIST_DENSE_GAUSSIAN, DIST_PRODUCT_OF_T, DIST_MULTIMODAL = range(8)
 SAMPLER_DISCRETE, SAMPLER_CONTINUOUS_TIME, SAMPLER_MARKOV_JUMP = range(3)
 RNG_PHILOX, RNG_INJECT = 0, 1
 CNT_L, CNT_F, CNT_FL, CNT_R, CNT_E, CNT_DEDX, CNT_FAIL, CNT_EXEC = range(8)

@@ -45,7 +45,9 @@ static fused_launch_fn find_fused(int dtype, int kind, int D) {
     return f;
 }
 
-static bool is_elementwise(int kind) { return kind >= MJHMC_DIST_TEST_GAUSSIAN && kind <= MJHMC_DIST_FUNNEL_LITERAL; }
+static bool is_elementwise(int kind) {
+    return (kind >= MJHMC_DIST_TEST_GAUSSIAN && kind <= MJHMC_DIST_FUNNEL_LITERAL) || kind == MJHMC_DIST_MULTIMODAL;
+}
 static bool is_dense(int kind) { return kind == MJHMC_DIST_DENSE_GAUSSIAN || kind == MJHMC_DIST_PRODUCT_OF_T; }
 
 static int fill_hp(LaunchParams& p, const mjhmc_hp* hp) {
@@ -108,7 +110,7 @@ static int check_dist(const mjhmc_dist* dist) {
     if (!dist) return fail("dist is NULL");
     if (dist->dtype != MJHMC_F32 && dist->dtype != MJHMC_F64) return fail("bad dtype");
     if (dist->ndims <= 0) return fail("ndims must be positive");
-    if (dist->kind < MJHMC_DIST_TEST_GAUSSIAN || dist->kind > MJHMC_DIST_PRODUCT_OF_T) return fail("bad distribution kind");
+    if (dist->kind < MJHMC_DIST_TEST_GAUSSIAN || dist->kind > MJHMC_DIST_MULTIMODAL) return fail("bad distribution kind");
     if ((dist->kind == MJHMC_DIST_DIAG_GAUSSIAN || is_dense(dist->kind)) && !dist->a0) return fail("distribution needs a0");
     if (dist->kind == MJHMC_DIST_PRODUCT_OF_T && (!dist->a1 || !dist->a2 || dist->nbasis <= 0)) return fail("ProductOfT needs a1, a2, nbasis");
     return 0;

@@ -17,6 +17,9 @@ namespace mjhmc {
 template <typename T> __device__ __forceinline__ T t_cospi(T x);
 template <> __device__ __forceinline__ double t_cospi<double>(double x) { return cospi(x); }
 template <> __device__ __forceinline__ float t_cospi<float>(float x) { return cospif(x); }
+template <typename T> __device__ __forceinline__ T t_log(T x);
+template <> __device__ __forceinline__ double t_log<double>(double x) { return log(x); }
+template <> __device__ __forceinline__ float t_log<float>(float x) { return logf(x); }
 template <typename T> __device__ __forceinline__ T t_exp(T x);
 template <> __device__ __forceinline__ double t_exp<double>(double x) { return exp(x); }
 template <> __device__ __forceinline__ float t_exp<float>(float x) { return expf(x); }
@@ -204,6 +207,32 @@ struct FunnelD {
         const T s = sumsq(x);
         if (LITERAL) return -(nk * x[0] * x[0] * inv_s2 + e * s);
         return x[0] * x[0] * ((T)0.5 * inv_s2) + (T)0.5 * e * s + (T)0.5 * nk * x[0];
+    }
+};
+
+// MultimodalGaussian (distributions.py:314-335): the separation vector is (2 sep, 0, ..., 0), so
+//   E = -log( exp(-|x + s|^2) + exp(-|x - s|^2) ),   c = exp(4 s.x),   g = 2 ((x - s) c + s + x) / (c + 1)
+// written as in the reference (the two exponentials under the log, the common factor c over all dims).
+template <typename T, int D>
+struct MultimodalD {
+    static constexpr int kind = MJHMC_DIST_MULTIMODAL;
+    static constexpr bool kLinear = false;
+    T s0;
+    __device__ __forceinline__ explicit MultimodalD(const LaunchParams& p) : s0((T)(2.0 * p.dp[0])) {}
+    __device__ __forceinline__ void grad(const T (&x)[D], T (&g)[D]) const {
+        const T c = t_exp<T>((T)4 * s0 * x[0]);
+        const T den = c + (T)1;
+        g[0] = ((T)2 * ((x[0] - s0) * c + s0 + x[0])) / den;
+#pragma unroll
+        for (int k = 1; k < D; ++k) g[k] = ((T)2 * (x[k] * c + x[k])) / den;
+    }
+    __device__ __forceinline__ T energy(const T (&x)[D]) const {
+        T rest = (T)0;
+#pragma unroll
+        for (int k = 1; k < D; ++k) rest += x[k] * x[k];
+        const T a = (x[0] + s0) * (x[0] + s0) + rest;
+        const T b = (x[0] - s0) * (x[0] - s0) + rest;
+        return -t_log<T>(t_exp<T>(-a) + t_exp<T>(-b));
     }
 };
 

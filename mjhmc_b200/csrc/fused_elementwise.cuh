@@ -294,6 +294,7 @@ fused_launch_fn pick_dist(int kind) {
         case MJHMC_DIST_ROUGH_WELL:     return &launch_fused<RoughWellD<T, D>, T, D>;
         case MJHMC_DIST_FUNNEL:         return &launch_fused<FunnelD<T, D, false>, T, D>;
         case MJHMC_DIST_FUNNEL_LITERAL: return &launch_fused<FunnelD<T, D, true>, T, D>;
+        case MJHMC_DIST_MULTIMODAL:     return &launch_fused<MultimodalD<T, D>, T, D>;
         default: return nullptr;
     }
 }

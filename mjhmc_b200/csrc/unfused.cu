@@ -45,6 +45,14 @@ __global__ void __launch_bounds__(kThreads) energy_kernel(DistParams dp, const T
             if (dp.kind == MJHMC_DIST_FUNNEL_LITERAL) e = -(nk * x0 * x0 * inv_s2 + ex * s);
             else e = x0 * x0 * ((T)0.5 * inv_s2) + (T)0.5 * ex * s + (T)0.5 * nk * x0;
         } break;
+        case MJHMC_DIST_MULTIMODAL: {                           // distributions.py:323-327
+            const T s0 = (T)(2.0 * dp.p[0]);
+            const T x0 = X[i];
+            T rest = (T)0;
+            for (int k = 1; k < d; ++k) { const T x = X[k * ld + i]; rest += x * x; }
+            const T a = (x0 + s0) * (x0 + s0) + rest, b = (x0 - s0) * (x0 - s0) + rest;
+            e = -t_log<T>(t_exp<T>(-a) + t_exp<T>(-b));
+        } break;
         case MJHMC_DIST_DENSE_GAUSSIAN: {
             const T* S = (const T*)dp.a0;                       // (J + J^T)/2, row-major
             for (int k = 0; k < d; ++k) {
@@ -107,6 +115,14 @@ __global__ void __launch_bounds__(kThreads) gradient_kernel(DistParams dp, const
                 G[i] = x0 * inv_s2 - (T)0.5 * ex * s + (T)0.5 * nk;
                 for (int k = 1; k < d; ++k) G[k * ld + i] = X[k * ld + i] * ex;
             }
+        } break;
+        case MJHMC_DIST_MULTIMODAL: {                           // distributions.py:329-335
+            const T s0 = (T)(2.0 * dp.p[0]);
+            const T x0 = X[i];
+            const T c = t_exp<T>((T)4 * s0 * x0);
+            const T den = c + (T)1;
+            G[i] = ((T)2 * ((x0 - s0) * c + s0 + x0)) / den;
+            for (int k = 1; k < d; ++k) { const T x = X[k * ld + i]; G[k * ld + i] = ((T)2 * (x * c + x)) / den; }
         } break;
         case MJHMC_DIST_DENSE_GAUSSIAN: {
             const T* S = (const T*)dp.a0;

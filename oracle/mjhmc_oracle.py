@@ -97,6 +97,26 @@ class RoughWellEnergy(Energy):
         return X / self.scale1 ** 2 + -sinX * 2 * np.pi / self.scale2
 
 
+class MultimodalGaussianEnergy(Energy):
+    """distributions.py:314-335: two unit Gaussians at -/+ sep_vec, sep_vec = (2 * separation, 0, ..., 0)
+    (row 0 of the reference's array holds ``separation`` and gets ``+= separation``, :316-319)."""
+    name = "MultimodalGaussian"
+
+    def __init__(self, separation=3, ndims=2):
+        self.separation = separation
+        self.sep = np.zeros((ndims, 1))
+        self.sep[0, 0] = 2 * separation
+
+    def E(self, X):
+        with np.errstate(over='ignore', divide='ignore'):
+            return -np.log(np.exp(-np.sum((X + self.sep) ** 2, axis=0)) + np.exp(-np.sum((X - self.sep) ** 2, axis=0)))
+
+    def dEdX(self, X):
+        with np.errstate(over='ignore', invalid='ignore'):
+            common_exp = np.exp(np.sum(4 * self.sep * X, axis=0))
+            return (2 * ((X - self.sep) * common_exp + self.sep + X)) / (common_exp + 1)
+
+
 class ProductOfTEnergy(Energy):
     """distributions.py:398-406 (float32 parameters) and :428-433 (energy).
 

@@ -32,6 +32,8 @@ def energy_from_golden(g):
         return orc.TestGaussianEnergy(p[0])
     if dist == "Gaussian":
         return orc.GaussianEnergy(p)
+    if dist == "MultimodalGaussian":
+        return orc.MultimodalGaussianEnergy(p[0], g["X0"].shape[0])
     raise KeyError(dist)
 
 
@@ -67,6 +69,8 @@ def product_distribution(dist_name, params, d, N):
         return D.TestGaussian(ndims=d, nbatch=N, sigma=params[0])
     if dist_name == "Gaussian":
         return D.Gaussian(ndims=d, nbatch=N, J=np.asarray(params))
+    if dist_name == "MultimodalGaussian":
+        return D.MultimodalGaussian(ndims=d, nbatch=N, separation=params[0])
     raise KeyError(dist_name)
 
 

@@ -175,6 +175,8 @@ def test_energy_gradient_kernels_match_oracle():
         (D.Gaussian(5, 50, log_conditioning=3), orc.GaussianEnergy.log_conditioned(5, 3), 5),
         (D.Gaussian(6, 50, J=J), orc.GaussianEnergy(J), 6),
         (D.Gaussian(40, 50, log_conditioning=2), orc.GaussianEnergy.log_conditioned(40, 2), 40),
+        (D.MultimodalGaussian(ndims=4, nbatch=50, separation=1), orc.MultimodalGaussianEnergy(1, 4), 4),
+        (D.MultimodalGaussian(ndims=20, nbatch=50, separation=0.5), orc.MultimodalGaussianEnergy(0.5, 20), 20),
         (D.Funnel(scale=3.0, nbatch=50, ndims=6), orc.FunnelEnergy(3.0), 6),
         (D.Funnel(scale=1.5, nbatch=50, ndims=6, literal_reference_energy=True), orc.FunnelEnergy(1.5, True), 6),
         (D.ProductOfT(ndims=7, nbasis=7, nbatch=50, W=W, lognu=np.log(nu), b=rs.randn(7) * 0.1),

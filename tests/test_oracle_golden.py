@@ -118,6 +118,7 @@ def test_resample_indices_match_reference_loop():
     (orc.FunnelEnergy(scale=1.5, literal=True), 5),
     (orc.RoughWellEnergy(100, 4), 3),
     (orc.GaussianEnergy(np.random.RandomState(3).randn(4, 4)), 4),
+    (orc.MultimodalGaussianEnergy(1, 3), 3),
 ])
 def test_gradients_match_finite_differences(energy, d):
     rs = np.random.RandomState(7)
