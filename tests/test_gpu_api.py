@@ -282,3 +282,27 @@ def test_pipelined_sample_equals_single_launch():
     np.testing.assert_array_equal(outs[0][0], outs[1][0])
     assert outs[0][1] == outs[1][1]
     assert outs[0][2] == 1 and outs[1][2] == 8
+
+
+def test_autocorrelation_curve_and_moments_agree_statistically_with_the_oracle():
+    """north_star's second check: with DIFFERENT random streams the GPU sampler and the numpy oracle must agree in
+    distribution -- the fft_autocor curve (autocor.py:37-49) over the first 40 lags and the first two moments.
+    Tolerances are 3.5x the largest difference seen between oracle runs with different seeds (0.017 on the curve,
+    0.8 % on the second moment) at this size."""
+    from mjhmc_b200.misc.distributions import RoughWell
+    from mjhmc_b200.samplers.markov_jump_hmc import MarkovJumpHMC
+    N, T = 4000, 120
+    rs = np.random.RandomState(1234)
+    X0, V0 = rs.randn(2, N) * 3, rs.randn(2, N)
+    hp = dict(epsilon=0.3, beta=0.2, num_leapfrog_steps=5)
+    dist = helpers.pin_init(RoughWell(2, N, scale1=5, scale2=4), X0)
+    s = MarkovJumpHMC(distribution=dist, V=V0, seed=77, resample=False, **hp)
+    X = s.sample(T, preserve_order=True)                       # (d, N, T)
+    o = orc.OracleSampler("MarkovJumpHMC", orc.RoughWellEnergy(5, 4), X0, V=V0, draws=orc.PhiloxDraws(3),
+                          resample=False, **hp)
+    Xo = o.sample(T, preserve_order=True)
+    assert X.shape == Xo.shape == (2, N, T)
+    ac, aco = orc.fft_autocor(X), orc.fft_autocor(Xo)
+    assert np.max(np.abs(ac[:40] - aco[:40])) < 0.06
+    assert abs(X.mean() - Xo.mean()) < 0.15
+    assert abs((X ** 2).mean() / (Xo ** 2).mean() - 1.0) < 0.03
