@@ -30,8 +30,15 @@ def calculate_autocorrelation(sampler, distribution, num_steps=None, num_grad_st
     cached_var = None
     if use_cached_var:
         print("Using cached variance")
-        _, emc_var_estimate, true_var_estimate, _ = distribution.load_cache()
-        cached_var = emc_var_estimate if sampler.__name__ == "MarkovJumpHMC" else true_var_estimate
+        try:
+            _, emc_var_estimate, true_var_estimate, _ = distribution.load_cache()
+            cached_var = emc_var_estimate if sampler.__name__ == "MarkovJumpHMC" else true_var_estimate
+        except FileNotFoundError:
+            # the reference writes the cache inside every Distribution() constructor (distributions.py:96-149); here
+            # that burn-in is opt-in, so the file may not exist.  The default (fft) estimate below
+            # normalises by lag 0 and never reads the cached variance (autocor.py:107-111).
+            print("Warning: no fair-initialisation cache for this distribution "
+                  "(distribution.cached_init_X() generates it); continuing without a cached variance")
 
     print("Calculating autocorrelation...")
     return autocorrelation(samples, e_evals, grad_evals, half_window, cached_var=cached_var)
@@ -157,7 +164,14 @@ def generate_samples(sampler, distribution, num_steps=None, num_grad_steps=None,
     while done < num_steps and stop is None:
         m = min(chunk, num_steps - done)
         snap = smp._snapshot()
-        S, e_c, g_c = _advance_with_trace(smp, distribution, m)
+        try:
+            S, e_c, g_c = _advance_with_trace(smp, distribution, m)
+        except _BackoffInChunk:
+            # a MarkovJumpHMC infinite-rate back-off (markov_jump_hmc.py:376-389) fired inside the chunk: its extra
+            # attempt breaks the one-iteration-per-step bookkeeping of the trace, so this chunk is redone with the
+            # reference's literal loop (one step + one counter read at a time, autocor.py:245-248)
+            smp._restore(snap)
+            S, e_c, g_c = _advance_stepwise(smp, distribution, m)
         if num_grad_steps is not None:
             hit = np.nonzero(g_c >= num_grad_steps)[0]
             if len(hit) and hit[0] < m - 1:
@@ -188,6 +202,21 @@ def _finish(samples, e_evals, grad_evals, return_device):
     return samples, e_evals, grad_evals
 
 
+class _BackoffInChunk(Exception):
+    pass
+
+
+def _advance_stepwise(smp, distribution, m):
+    """m iterations, one launch and one counter read per step (the reference's loop, autocor.py:245-248)."""
+    n = float(distribution.nbatch)
+    parts, e_c, g_c = [], np.zeros(m), np.zeros(m)
+    for t in range(m):
+        parts.append(smp._advance(1)[0])
+        g_c[t] = distribution.dEdX_count / n
+        e_c[t] = distribution.E_count / n
+    return torch.cat(parts, dim=1), e_c, g_c
+
+
 def _advance_with_trace(smp, distribution, m):
     """m iterations in one launch; returns the samples and E_count/n, dEdX_count/n after every iteration.
 
@@ -205,8 +234,7 @@ def _advance_with_trace(smp, distribution, m):
         uncached0 = int((smp._engine.ca[smp._engine.cur] & 1).eq(0).sum().item())
     S, _, choice = smp._advance(m, want_choice=mj)
     if smp._attempt - a0 != m:
-        raise RuntimeError("generate_samples: an infinite-rate back-off occurred inside a traced chunk; "
-                           "use a smaller step size or call sample() step by step")
+        raise _BackoffInChunk()
     per_iter = np.full(m, distribution.nbatch, dtype=np.int64)
     if mj:
         moved_off_cache = (choice != 0).sum(dim=1).cpu().numpy().astype(np.int64)      # F or R moves per iteration

@@ -9,6 +9,13 @@ particle index -- results do not depend on G.  NCCL (gloo in the CPU tests) is u
   * samples, when the caller wants the full array     -> all_gather
 The batch-wide R coin of the discrete samplers needs no exchange: it is drawn from a
 particle-independent Philox counter, so every rank computes the same coin.
+
+Samplers built with ``sharded=True`` (or ``sharded=<process group>``) also take the reference's two other
+batch-global couplings over the whole cloud, so a sharded run equals the single-GPU run:
+  * MarkovJumpHMC's infinite-rate back-off (markov_jump_hmc.py:376-389)   -> all_reduce(MIN) of the first failing
+    iteration after every launch: all ranks replay, count and retry at the same iteration
+  * dwell-time resampling (markov_jump_hmc.py:321-328)                    -> all_gather of the per-(iteration, rank)
+    dwell sums + one broadcast of the sorted uniforms (resample_plan), then the local resampling kernel
 """
 import ctypes as C
 
@@ -25,6 +32,90 @@ def world(group=None):
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(group), dist.get_world_size(group)
     return 0, 1
+
+
+def resolve_group(sharded):
+    """``sharded=True`` -> the default (WORLD) group; a process group is taken as is."""
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("sharded=... needs an initialised torch.distributed process group")
+    return dist.group.WORLD if sharded is True else sharded
+
+
+def allreduce_min(value, group=None):
+    """min over the ranks of one int64 (the first failing iteration of a launch, INT64_MAX = none)."""
+    rank, ws = world(group)
+    if ws == 1:
+        return int(value)
+    t = torch.tensor([int(value)], dtype=torch.int64, device=_comm_device(group))
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return int(t.item())
+
+
+def allreduce_sum_int(value, group=None):
+    rank, ws = world(group)
+    if ws == 1:
+        return int(value)
+    t = torch.tensor([int(value)], dtype=torch.int64, device=_comm_device(group))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return int(t.item())
+
+
+def resample_plan(seg_sums, m_out, group=None, uniforms=None):
+    """Global offsets for dwell-time resampling of a sharded cloud (markov_jump_hmc.py:321-328).
+
+    seg_sums: (n_iter,) float64, dwell sum of the LOCAL particles per iteration.  The reference's cumulative sum
+    runs over the flat order (iteration-major, particle-minor over the whole cloud), in which the local particles
+    of iteration `it` form one contiguous segment.  Returns a dict with
+      r       (m_out,) sorted uniforms * total dwell time -- np.sort(np.random.random(m_out)) drawn on rank 0 and
+              broadcast (or `uniforms`, already sorted, for tests), identical on every rank
+      bounds  (2 n_iter,) [A_0, B_0, A_1, B_1, ...]: this rank's segment `it` covers cumulative times [A_it, B_it)
+      gaps    (n_iter,) A_it - B_{it-1}: dwell mass owned by other ranks between two consecutive local segments
+      total   total dwell time of the cloud
+    """
+    rank, ws = world(group)
+    seg = seg_sums.detach().double()
+    n_iter = seg.numel()
+    if ws > 1:
+        dev = _comm_device(group)
+        mine = seg.to(dev).contiguous()
+        parts = [torch.empty_like(mine) for _ in range(ws)]
+        dist.all_gather(parts, mine, group=group)
+        table = torch.stack(parts, dim=1).cpu().numpy()          # (n_iter, ws)
+    else:
+        table = seg.cpu().numpy().reshape(n_iter, 1)
+    incl = np.cumsum(table.reshape(-1)).reshape(n_iter, ws)      # inclusive prefix over (iteration, rank) segments
+    total = float(incl[-1, -1]) if incl.size else 0.0
+    excl = np.concatenate(([0.0], incl.reshape(-1)[:-1])).reshape(n_iter, ws)
+    A, B = excl[:, rank], incl[:, rank]
+    bounds = np.stack((A, B), axis=1).reshape(-1)
+    gaps = A - np.concatenate(([0.0], B[:-1]))
+    if uniforms is None:
+        if ws > 1:
+            dev = _comm_device(group)
+            u = torch.empty(m_out, dtype=torch.float64, device=dev)
+            if rank == 0:
+                u.copy_(torch.as_tensor(np.sort(np.random.random(m_out))))
+            dist.broadcast(u, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            uniforms = u.cpu().numpy()
+        else:
+            uniforms = np.sort(np.random.random(m_out))
+    return dict(r=np.asarray(uniforms) * total, bounds=bounds, gaps=gaps, total=total)
+
+
+def allgather_resampled(local_cols, columns, m_out, group=None):
+    """Assembles the reference's resampled array (ndims, m_out) from the per-rank parts a sharded
+    ``sample()`` returns: local_cols (ndims, k) numpy and their positions ``sampler.resample_columns``."""
+    rank, ws = world(group)
+    d = local_cols.shape[0]
+    out = np.zeros((d, m_out))
+    if ws == 1:
+        out[:, columns] = local_cols
+        return out
+    payload = [None] * ws
+    dist.all_gather_object(payload, (np.asarray(columns), np.asarray(local_cols)), group=group)
+    for cols, vals in payload:
+        out[:, cols] = vals
+    return out
 
 
 def shard_bounds(n_global, rank, world_size):

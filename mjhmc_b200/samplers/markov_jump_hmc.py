@@ -16,6 +16,10 @@ B200-specific keyword arguments (all optional, accepted by every class):
     device           torch device string, default current CUDA device
     injected_draws   dict(Z=(A,d,N), U=(A,3,N), U0=(A,)) -> INJECT mode (trajectory parity tests)
     particle_offset  global index of this shard's first particle (multi-GPU sharding)
+    sharded          True or a torch.distributed process group: this sampler holds one shard of a particle cloud
+                     spread over the ranks of the group; the batch-global couplings of the reference (infinite-rate
+                     back-off markov_jump_hmc.py:376-389, dwell-time resampling :321-328) are then taken over the
+                     WHOLE cloud (mjhmc_b200/parallel.py), so results do not depend on the number of ranks
     V                initial momentum (default np.random.randn like hmc_state.py:26)
 """
 import ctypes as C
@@ -23,7 +27,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from .. import _device, _lib
+from .. import _device, _lib, parallel
 from ..misc.distributions import Distribution
 from ..misc.utils import overrides
 from .hmc_state import HMCState
@@ -37,7 +41,7 @@ INFINITE_RATE_MSG = ("Infinite rate. This occurs when calculating transition rat
                      "Try decreasing the leapfrog stepsize/number of steps or dividing "
                      " the energy by a large constant.")
 
-_B200_KWARGS = ("dtype", "seed", "device", "injected_draws", "particle_offset", "V", "kernel")
+_B200_KWARGS = ("dtype", "seed", "device", "injected_draws", "particle_offset", "V", "kernel", "sharded")
 
 
 class _CallableEnergy(Distribution):
@@ -116,7 +120,9 @@ class _Engine(object):
             tmpl[:_lib.COUNTER_STRIPES, _lib.CNT_FAIL] = _lib.INT64_MAX
             self.cnt_template = torch.as_tensor(tmpl, device=self.device)
             self.counters = self.cnt_template.clone()
-            self.dwell_last = torch.zeros(self.n, dtype=torch.float64, device=self.device)
+            # double-buffered like the state: a launch that is not committed (failed attempt, counting launch)
+            # must leave sampler.dwelling_times untouched, as the reference does when draw_from raises
+            self.dwell = [torch.zeros(self.n, dtype=torch.float64, device=self.device) for _ in range(2)]
             if not self.fused:
                 # the reference's full HMCState (hmc_state.py:28-39): callables cannot be re-evaluated on chip
                 self.G = self._callback(self.X[0], True, count=False)
@@ -124,6 +130,10 @@ class _Engine(object):
                 self.EV = self._kinetic(self.V[0])
         self.launches = 0
         self.kernel_events = None
+        # (epsilon, L) of the committed launch that may have left "energy valid" flags without cache_active
+        # (flag value 2, set by an F move: H_cache = H_L at THAT epsilon / L); None = no such flags exist
+        self._cache_key = None
+        self._launch_key = None
 
     # ---------------------------------------------------------------- helpers
     def ctx(self):
@@ -183,7 +193,7 @@ class _Engine(object):
             o.dwell = dwell.data_ptr() + it0 * self.n * 8
         if choice is not None:
             o.choice = choice.data_ptr() + it0 * self.n
-        o.dwell_last = self.dwell_last.data_ptr()
+        o.dwell_last = self.dwell[self.cur ^ 1 if self.fused else self.cur].data_ptr()
         o.counters = self.counters.data_ptr()
         return o
 
@@ -192,8 +202,27 @@ class _Engine(object):
         _lib.check(self.lib.mjhmc_counters_read(_device.ptr(self.counters), out, self._stream()), "counters_read")
         return list(out)
 
+    @property
+    def dwell_last(self):
+        return self.dwell[self.cur]
+
     def reset_cache(self):
         self.ca[self.cur].zero_()
+        self._cache_key = None
+
+    def _drop_stale_flf_energies(self):
+        """The kernels keep H_L as the FLF energy of a particle that took an F move (flag 2: FLF(F z) = F L z).
+        That energy belongs to the (epsilon, L) it was integrated with: after the infinite-rate back-off
+        (markov_jump_hmc.py:376-389) or when the caller edits sampler.epsilon / num_leapfrog_steps the reference
+        re-integrates with the new values (cache_active is False there), so those flags are dropped.  Flags of
+        L movers (3) stay: the reference keeps their cached pre-move state whatever the hyper-parameters."""
+        s = self.sampler
+        key = (float(s.epsilon), int(s.num_leapfrog_steps))
+        if self._cache_key is not None and key != self._cache_key:
+            ca = self.ca[self.cur]
+            ca.masked_fill_(ca == 2, 0)
+            self._cache_key = None
+        self._launch_key = key
 
     # ---------------------------------------------------------------- fused launch
     def launch(self, attempt0, n_iter, samples=None, it0=0, dwell=None, choice=None):
@@ -202,6 +231,8 @@ class _Engine(object):
         with torch.cuda.device(self.device):
             self.counters.copy_(self.cnt_template)
             if self.fused:
+                if self.sampler._sampler_code == _lib.SAMPLER_MARKOV_JUMP:
+                    self._drop_stale_flf_energies()
                 hp, rng = self._hp(), self._rng(attempt0)
                 if self.inj is not None and attempt0 + n_iter > self.inj["U"].shape[0]:
                     raise IndexError("injected draws exhausted")
@@ -223,6 +254,7 @@ class _Engine(object):
     def commit(self):
         if self.fused:
             self.cur ^= 1
+            self._cache_key = self._launch_key
 
     # ---------------------------------------------------------------- unfused (callback) path
     def _callback(self, Xd, want_grad, count=True):
@@ -281,7 +313,7 @@ class _Engine(object):
             Gp, EXp, EVp = self._L(Xp, Vp, self.G.clone())
             snap = None
             if s._sampler_code != _lib.SAMPLER_DISCRETE:
-                snap = [t.clone() for t in (X, V, self.G, self.EX, self.EV, self.Hc[0], self.ca[0])]
+                snap = [t.clone() for t in (X, V, self.G, self.EX, self.EV, self.Hc[0], self.ca[0], self.dwell[0])]
             cur = _lib.FullState(X.data_ptr(), V.data_ptr(), self.G.data_ptr(), self.EX.data_ptr(), self.EV.data_ptr())
             prop = _lib.FullState(Xp.data_ptr(), Vp.data_ptr(), Gp.data_ptr(), EXp.data_ptr(), EVp.data_ptr())
             hp, rng = self._hp(), self._rng(attempt0 + it)
@@ -294,7 +326,7 @@ class _Engine(object):
             self.launches += 1
             cnt = self._read_counters()
             if cnt[_lib.CNT_FAIL] != _lib.INT64_MAX:
-                for dst, src in zip((X, V, self.G, self.EX, self.EV, self.Hc[0], self.ca[0]), snap):
+                for dst, src in zip((X, V, self.G, self.EX, self.EV, self.Hc[0], self.ca[0], self.dwell[0]), snap):
                     dst.copy_(src)
                 total[_lib.CNT_FAIL] = it
                 return total
@@ -314,6 +346,7 @@ class _Engine(object):
         self.V[c].copy_(_device.to_device(st.V, self.dtype, self.device))
         self.ca[c].copy_(torch.as_tensor(np.asarray(st.cache_active, dtype=np.uint8) * 3, device=self.device))
         self.Hc[c].copy_(_device.to_device(st.H_cache, self.dtype, self.device))
+        self._cache_key = None
         if not self.fused:
             self.G = self._callback(self.X[0], True, count=False)
             self.EX = self._callback(self.X[0], False, count=False).reshape(-1)
@@ -335,6 +368,8 @@ class HMCBase(object):
         if unknown:
             raise TypeError("__init__() got an unexpected keyword argument %r" % sorted(unknown)[0])
         self._opts = b200
+        sharded = b200.get("sharded")
+        self._group = None if not sharded else parallel.resolve_group(sharded)
         self._engine = None
         self._host_state = None
         self._attempt = 0
@@ -464,6 +499,12 @@ class HMCBase(object):
             m = n - done
             cnt = eng.launch(self._attempt, m, samples, it0 + done, dwell, choice)
             fail = cnt[_lib.CNT_FAIL]
+            if self._group is not None:
+                # the back-off is batch-wide in the reference (markov_jump_hmc.py:376-389): every rank replays,
+                # counts and retries at the first failing iteration of the WHOLE cloud
+                if not eng.fused:
+                    raise NotImplementedError("sharded runs need a fused energy (callables advance in place)")
+                fail = parallel.allreduce_min(fail, self._group)
             if fail == _lib.INT64_MAX:
                 eng.commit()
                 self._accumulate(cnt)
@@ -513,7 +554,7 @@ class HMCBase(object):
         tensors = [t.clone() for t in (eng.X[c], eng.V[c], eng.Hc[c], eng.ca[c], eng.dwell_last)]
         ints = (self._attempt, self.l_count, self.f_count, self.fl_count, self.r_count, d.E_count, d.dEdX_count,
                 self.grad_evals_executed)
-        return tensors, ints
+        return tensors, ints, eng._cache_key
 
     def _restore(self, snap):
         eng, d = self._engine, self.distribution
@@ -522,6 +563,7 @@ class HMCBase(object):
             dst.copy_(src)
         (self._attempt, self.l_count, self.f_count, self.fl_count, self.r_count, d.E_count, d.dEdX_count,
          self.grad_evals_executed) = snap[1]
+        eng._cache_key = snap[2]
         self._host_state = None
 
     def sampling_iteration(self):
@@ -687,17 +729,56 @@ class ContinuousTimeHMC(HMCBase):
         S, dwell, _ = self._advance(n_samples + 1, want_dwell=True)
         n, N, d = n_samples, self.nbatch, self.ndims
         m = n * N
+        if self._group is not None:
+            return self._resample_sharded(S, dwell[:n], n)
         dwell_t = dwell[:n].reshape(-1)
         total_t = np.sum(dwell_t.cpu().numpy())
         r = np.sort(np.random.random(m)) * total_t
+        self.resample_columns = None
         with eng.ctx():
-            r_d = torch.as_tensor(r, device=eng.device)
-            out = torch.zeros((d, m), dtype=eng.tdtype, device=eng.device)
-            nbytes = int(eng.lib.mjhmc_resample_scratch_bytes(m))
-            scratch = torch.empty(nbytes, dtype=torch.uint8, device=eng.device)
-            _lib.check(eng.lib.mjhmc_resample(eng.code, d, _device.ptr(dwell_t), m, _device.ptr(r_d), m,
-                                              _device.ptr(S), S.stride(0), _device.ptr(out), m, None,
-                                              _device.ptr(scratch), eng._stream()), "resample")
+            out = self._resample_device(S, dwell_t, torch.as_tensor(r, device=eng.device))
+            return self._d2h(out).astype(np.float64, copy=False)
+
+    def _resample_device(self, S, dwell_t, r_d):
+        """out[:, j] = samples[:, first i with cumsum(dwell_t)[i] > r[j]] (markov_jump_hmc.py:321-328)."""
+        eng = self._engine
+        d, m, m_out = self.ndims, dwell_t.numel(), r_d.numel()
+        out = torch.zeros((d, m_out), dtype=eng.tdtype, device=eng.device)
+        if m == 0 or m_out == 0:
+            return out
+        nbytes = int(eng.lib.mjhmc_resample_scratch_bytes(m))
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=eng.device)
+        _lib.check(eng.lib.mjhmc_resample(eng.code, d, _device.ptr(dwell_t), m, _device.ptr(r_d), m_out,
+                                          _device.ptr(S), S.stride(0), _device.ptr(out), m_out, None,
+                                          _device.ptr(scratch), eng._stream()), "resample")
+        return out
+
+    def _resample_sharded(self, S, dwell, n):
+        """Dwell-time resampling over the WHOLE sharded cloud.  The reference's flat order is
+        iteration-major, particle-minor over all particles (np.concatenate(dwell_t_k), :321): one all_gather of
+        the per-(iteration, rank) dwell sums gives every local segment its global offset, the sorted uniforms are
+        drawn once (rank 0) and shared, and each rank resolves the draws that land in its own segments with the
+        single-GPU kernel.  Returns the resampled columns whose source particle lives on this rank, in increasing
+        column order; ``self.resample_columns`` holds their positions in the reference's (ndims, n * N) array
+        (parallel.allgather_resampled assembles it)."""
+        eng = self._engine
+        n_local = self.nbatch
+        with eng.ctx():
+            seg = dwell.sum(dim=1) if n_local else torch.zeros(n, dtype=torch.float64, device=eng.device)
+            plan = parallel.resample_plan(seg, n * parallel.allreduce_sum_int(n_local, self._group), self._group)
+            r_d = torch.as_tensor(plan["r"], device=eng.device)
+            # which draws fall into a segment of this rank: bounds = [A_0, B_0, A_1, B_1, ...] ascending
+            bounds = torch.as_tensor(plan["bounds"], device=eng.device)
+            pos = torch.searchsorted(bounds, r_d, right=True)
+            cols = torch.nonzero(pos % 2 == 1).reshape(-1)
+            self.resample_columns = cols.cpu().numpy()
+            if n_local == 0 or cols.numel() == 0:
+                return np.zeros((self.ndims, 0))
+            # fold the dwell mass other ranks own between two local segments into the first local element of the
+            # later one: the local prefix sums then ARE the global ones at every local element
+            dwell_g = dwell.clone()
+            dwell_g[:, 0] += torch.as_tensor(plan["gaps"], device=eng.device)
+            out = self._resample_device(S, dwell_g.reshape(-1), r_d[cols].contiguous())
             return self._d2h(out).astype(np.float64, copy=False)
 
 

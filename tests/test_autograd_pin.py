@@ -1,0 +1,81 @@
+"""Independent pin for the two hand-derived gradients of the oracle.
+
+The reference never writes these gradients down: ProductOfT asks Theano for ``T.grad(T.sum(energy), state)``
+(misc/distributions.py:410) and the Funnel asks TensorFlow for ``tf.gradients(energy_op, state_pl)``
+(misc/tf_distributions.py:89-91).  Neither framework is in this image, but reverse-mode differentiation of the
+same expression graph is exactly what ``torch.autograd`` computes: the reference's energy formulas are written
+here in torch operation by operation (misc/distributions.py:428-433, misc/tf_distributions.py:161-165) and
+differentiated; the oracle's closed-form energies and gradients (oracle/mjhmc_oracle.py: ProductOfTEnergy,
+FunnelEnergy) must agree to rounding.  CPU only, float64.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mjhmc_oracle as orc
+
+
+def _pot_energy_torch(X, W, nu, b):
+    """misc/distributions.py:428-433, line by line (X: [ndims, n])."""
+    rshp_b = b.reshape((1, -1))
+    rshp_nu = nu.reshape((1, -1))
+    alpha = (rshp_nu + 1.) / 2.
+    energy_per_expert = alpha * torch.log(1 + ((torch.matmul(X.T, W) + rshp_b) / rshp_nu) ** 2)
+    return torch.sum(energy_per_expert, dim=1).reshape((1, -1))
+
+
+def _funnel_literal_energy_torch(X, scale):
+    """misc/tf_distributions.py:161-165 as written: e_x_0 [n] broadcasts over the ndims - 1 rows of e_x_k."""
+    e_x_0 = -((X[0, :] ** 2) / (scale ** 2))
+    e_x_k = -((X[1:, :] ** 2) / torch.exp(X[0, :]))
+    return torch.sum(e_x_0 + e_x_k, dim=0)
+
+
+def _funnel_neal_energy_torch(X, scale):
+    """-log density of the distribution the reference docstring states (misc/tf_distributions.py:143-147):
+    x_0 ~ N(0, scale^2), x_i ~ N(0, e^{x_0}) (variance), additive constants dropped."""
+    d = X.shape[0]
+    return X[0] ** 2 / (2 * scale ** 2) + 0.5 * torch.exp(-X[0]) * torch.sum(X[1:] ** 2, dim=0) + (d - 1) * X[0] / 2
+
+
+def _autograd(fn, X):
+    Xt = torch.tensor(X, dtype=torch.float64, requires_grad=True)
+    E = fn(Xt)
+    G, = torch.autograd.grad(E.sum(), Xt)              # T.grad(T.sum(energy), state) / tf.gradients(energy, state)
+    return E.detach().numpy().reshape(-1), G.numpy()
+
+
+@pytest.mark.parametrize("d,kind", [(6, "identity"), (36, "sparse"), (100, "sparse"), (100, "dense")])
+def test_product_of_t_gradient_is_the_autodiff_of_the_reference_energy(d, kind):
+    rs = np.random.RandomState(2015 + d)
+    if kind == "identity":
+        W = np.eye(d)
+    elif kind == "sparse":                             # search/MJHMC_poe_36/mjhmc_objective.py:15-23
+        W = rs.randn(d, d)
+        W[rs.rand(d, d) > 0.05] = 0
+        W += np.eye(d) * 0.5
+    else:
+        W = rs.randn(d, d) / np.sqrt(d)
+    W = W.astype(np.float32).astype(np.float64)        # parameters are float32 in the reference (:398-406)
+    nu = (rs.rand(d) * 2 + 2.1).astype(np.float32).astype(np.float64)
+    b = (rs.randn(d) * 0.3).astype(np.float32).astype(np.float64)
+    X = rs.randn(d, 257) * 2.0
+    en = orc.ProductOfTEnergy(W, nu, b)
+    E_ref, G_ref = _autograd(lambda x: _pot_energy_torch(x, torch.tensor(W), torch.tensor(nu), torch.tensor(b)), X)
+    np.testing.assert_allclose(np.asarray(en.E(X)).reshape(-1), E_ref, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(en.dEdX(X), G_ref, rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("scale", [1.0, 3.0])
+@pytest.mark.parametrize("d", [2, 10])
+def test_funnel_gradients_are_the_autodiff_of_the_reference_graph(scale, d):
+    rs = np.random.RandomState(7 * d)
+    X = np.vstack((rs.randn(1, 300) * scale, rs.randn(d - 1, 300) * 2.0))
+    lit = orc.FunnelEnergy(scale, literal=True)
+    E_ref, G_ref = _autograd(lambda x: _funnel_literal_energy_torch(x, scale), X)
+    np.testing.assert_allclose(np.asarray(lit.E(X)).reshape(-1), E_ref, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(lit.dEdX(X), G_ref, rtol=1e-12, atol=1e-12)
+    neal = orc.FunnelEnergy(scale, literal=False)
+    E_ref, G_ref = _autograd(lambda x: _funnel_neal_energy_torch(x, scale), X)
+    np.testing.assert_allclose(np.asarray(neal.E(X)).reshape(-1), E_ref, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(neal.dEdX(X), G_ref, rtol=1e-12, atol=1e-12)

@@ -103,7 +103,7 @@ def test_stream_agrees_with_register_kernel(kind, d, dtype):
     else:
         X, Xo = res[0][0], res[1][0]
         same = np.all(np.abs(X - Xo) <= 1e-3 * (1 + np.abs(Xo)), axis=0)
-        assert same.mean() > 0.97 and helpers.rel_err(X[:, same], Xo[:, same]) < 1e-4
+        assert same.mean() > 0.97 and helpers.rel_err32(X[:, same], Xo[:, same]) < 1e-4
 
 
 def test_stream_one_launch_equals_many():
@@ -178,7 +178,7 @@ def test_stream_kernel_fp32_with_several_threads_per_particle(kind, d):
     s, dist, o = _pair(kind, dist_name, d, 1500, 40 + d, hp, dtype="float32")
     X, Xo = s.sample(1), o.sample(1)
     same = np.all(np.abs(X - Xo) <= 1e-3 * (1 + np.abs(Xo)), axis=0)
-    assert same.mean() > 0.97 and helpers.rel_err(X[:, same], Xo[:, same]) < 1e-4
+    assert same.mean() > 0.97 and helpers.rel_err32(X[:, same], Xo[:, same]) < 1e-4
 
 
 @pytest.mark.parametrize("d", [6, 24, 100])

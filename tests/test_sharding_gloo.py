@@ -45,6 +45,38 @@ def _worker(rank, world_size, port, out):
         ref = orc.fft_autocor(np.ascontiguousarray(Xg.transpose(0, 2, 1)))
         np.testing.assert_allclose(ac, ref, atol=1e-12)
         assert abs(parallel.effective_sample_size(ac) - orc.ess_from_autocor(ref)) < 1e-9
+        # first failing iteration of a launch: min over the ranks (INT64_MAX = none) -> all ranks back off together
+        big = (1 << 63) - 1
+        assert parallel.allreduce_min(big) == big
+        assert parallel.allreduce_min(5 if rank == 1 else big) == 5
+        assert parallel.allreduce_min(3 + rank) == 3
+        assert parallel.allreduce_sum_int(hi - lo) == N
+        # dwell-time resampling over the sharded cloud: the plan reproduces the reference's global search
+        # (markov_jump_hmc.py:321-328) when every rank resolves the draws that land in its own segments
+        n_it = 5
+        dwell_g = rs.exponential(size=(n_it, N))
+        dwell_l = dwell_g[:, lo:hi]
+        u = np.sort(rs.random_sample(n_it * N))
+        plan = parallel.resample_plan(torch.as_tensor(dwell_l.sum(axis=1)), n_it * N, uniforms=u)
+        cumul = np.cumsum(dwell_g.reshape(-1))
+        assert abs(plan["total"] - cumul[-1]) < 1e-9
+        want = np.searchsorted(cumul, u * cumul[-1], side="right")           # global flat index it * N + i
+        own = (want % N >= lo) & (want % N < hi)
+        pos = np.searchsorted(plan["bounds"], plan["r"], side="right")
+        mine = pos % 2 == 1
+        np.testing.assert_array_equal(mine, own)
+        dl = dwell_l.copy()
+        dl[:, 0] += plan["gaps"]
+        got = np.searchsorted(np.cumsum(dl.reshape(-1)), plan["r"][mine], side="right")   # local flat index
+        np.testing.assert_array_equal((got // (hi - lo)) * N + lo + got % (hi - lo), want[own])
+        # shared uniforms: drawn on rank 0, identical everywhere
+        np.random.seed(100 + rank)
+        plan2 = parallel.resample_plan(torch.as_tensor(dwell_l.sum(axis=1)), 11)
+        np.random.seed(100)
+        np.testing.assert_array_equal(plan2["r"], np.sort(np.random.random(11)) * plan2["total"])
+        cols = np.nonzero(mine)[0]
+        full_r = parallel.allgather_resampled(np.vstack((cols, cols * 2.0)), cols, n_it * N)
+        np.testing.assert_array_equal(full_r[0], np.arange(n_it * N))
         if rank == 0:
             out.put("ok")
     finally:
