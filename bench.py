@@ -52,6 +52,9 @@ WORKLOADS = {
     "pot100d_mjhmc": dict(dist="ProductOfT", ndims=100, n=1_000_000, sampler="MarkovJumpHMC",
                           epsilon=0.4827975928783417, beta=0.10154356807470322, L=10, iters=2,
                           source="search/MJHMC_poe_100/params.json; dense W = randn/sqrt(100)"),
+    "pot100d_mjhmc_f32": dict(dist="ProductOfT", ndims=100, n=1_000_000, sampler="MarkovJumpHMC", dtype="float32",
+                              epsilon=0.4827975928783417, beta=0.10154356807470322, L=10, iters=2,
+                              source="search/MJHMC_poe_100/params.json; dense W = randn/sqrt(100); fp32 states, tcgen05 3xTF32"),
     # HBM-bound points of the fused leapfrog (one iteration per launch, L = 1)
     "testgauss2d_control_L1": dict(dist="TestGaussian", ndims=2, n=16_000_000, sampler="ControlHMC",
                                    epsilon=0.5, beta=0.1, L=1, iters=1, source="HBM roofline point"),
@@ -101,8 +104,6 @@ WORKLOADS = {
                                 source="search/MJHMC_funnel/config.json midpoints; ESS from fft_autocor over 256 recorded steps"),
 }
 DEFAULT_WORKLOAD = "roughwell2d_mjhmc"
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full captures (profiles/)
-TRAFFIC = {"roughwell2d_mjhmc": 46034944 + 1041338000}
 DTYPE = "float64"          # the reference's arithmetic
 METRIC = "particle_leapfrog_steps_per_s"
 UNIT = "particle-leapfrog-steps/s"
@@ -312,19 +313,42 @@ def _ess_from_curve(ac, T):
     return T / (1.0 + 2.0 * s)
 
 
-def make_sampler(w, rank, dtype=None, seed=2024):
+def _device_cloud(w, n, seed, dev, tdtype):
+    """The synthetic particle cloud of _init_cloud drawn on the device (the secondary workloads of the default
+    run: nothing of theirs is compared with the CPU arm, so the host need not hold a copy)."""
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    d = w["ndims"]
+    rn = lambda *shape: torch.randn(*shape, generator=g, device=dev, dtype=torch.float64)
+    if w["dist"] == "RoughWell":
+        X = 100 * rn(d, n)
+    elif w["dist"] == "Funnel":
+        x0 = 3.0 * rn(1, n)
+        X = torch.cat((x0, torch.exp(x0 / 2.) * rn(d - 1, n)), dim=0)
+    elif w["dist"] == "GaussianRot":
+        wv, Q = np.linalg.eigh(_rotated_J(d))
+        X = torch.as_tensor(Q, device=dev) @ (torch.as_tensor((1. / np.sqrt(wv)).reshape((-1, 1)), device=dev) * rn(d, n))
+    elif w["dist"] == "DiagGaussian" and w.get("log_cond", 1) != 1:
+        X = rn(d, n) / torch.as_tensor(np.sqrt(10 ** np.linspace(-w["log_cond"], 0, d)).reshape(-1, 1), device=dev)
+    else:
+        X = rn(d, n)
+    return X.to(tdtype), rn(d, n).to(tdtype)
+
+
+def make_sampler(w, rank, dtype=None, seed=2024, n=None, device_init=None):
     dtype = dtype or w.get("dtype", DTYPE)
     from mjhmc_b200.misc import distributions as D
     from mjhmc_b200.samplers import markov_jump_hmc as S
-    n, d = w["n"], w["ndims"]
+    n, d = n or w["n"], w["ndims"]
     if w["dist"] == "RoughWell":
-        dist = D.RoughWell(ndims=d, nbatch=n)
+        dist = D.RoughWell(ndims=d, nbatch=8)
     elif w["dist"] == "TestGaussian":
-        dist = D.TestGaussian(ndims=d, nbatch=n)
+        dist = D.TestGaussian(ndims=d, nbatch=8)
     elif w["dist"] == "DiagGaussian":
         dist = D.Gaussian(ndims=d, nbatch=8, log_conditioning=w.get("log_cond", 1))
     elif w["dist"] == "Funnel":
-        dist = D.Funnel(scale=3.0, ndims=d, nbatch=n)
+        dist = D.Funnel(scale=3.0, ndims=d, nbatch=8)
     elif w["dist"] == "GaussianRot":
         dist = D.Gaussian(ndims=d, nbatch=8, J=_rotated_J(d))
     elif w["dist"] == "ProductOfT":
@@ -333,7 +357,11 @@ def make_sampler(w, rank, dtype=None, seed=2024):
     else:
         raise KeyError(w["dist"])
     dist.nbatch = n
-    X0, V0 = _init_cloud(w, n, 1000 + rank)
+    if device_init is not None:
+        import torch
+        X0, V0 = _device_cloud(w, n, 1000 + rank, device_init, torch.float32 if dtype == "float32" else torch.float64)
+    else:
+        X0, V0 = _init_cloud(w, n, 1000 + rank)
     dist.gen_init_X = lambda: setattr(dist, "Xinit", X0)
     kw = dict(resample=False) if w["sampler"] in ("ContinuousTimeHMC", "MarkovJumpHMC") else {}
     if w.get("kernel"):
@@ -343,203 +371,370 @@ def make_sampler(w, rank, dtype=None, seed=2024):
     return s, dist, X0, V0
 
 
-def run_b200(args, w):
-    import torch
-    import torch.distributed as dist_pkg
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist_pkg.init_process_group("nccl", device_id=dev)
+class Ctx(object):
+    """Process-wide plumbing of one bench run: rank / world, device, barrier, the L2 flush buffer."""
 
-    def barrier():
-        if world > 1:
-            dist_pkg.barrier()
-        torch.cuda.synchronize()
+    def __init__(self):
+        import torch
+        import torch.distributed as dist_pkg
+        self.torch, self.dist = torch, dist_pkg
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        # one rank per GPU: give every rank its own slice of the host cores (the e2e path is a host-side memcpy
+        # pipeline; eight ranks bouncing over the same cores cost bandwidth)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = len(cores) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", self.world)))
+            if self.world > 1 and per >= 1:
+                os.sched_setaffinity(0, cores[self.local_rank * per:(self.local_rank + 1) * per])
+        except (AttributeError, OSError):
+            pass
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist_pkg.init_process_group("nccl", device_id=self.dev)
+        self.flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=self.dev)   # 256 MB > 126 MB L2
 
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = run_reference(w, steps=2, warmup=1)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    sampler, dist, X0, V0 = make_sampler(w, rank)
+    def reduce(self, vals, op, dtype):
+        t = self.torch.tensor(vals, dtype=dtype, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=op)
+        return t.tolist()
+
+    def max_f(self, *vals):
+        return self.reduce(list(vals), self.dist.ReduceOp.MAX, self.torch.float64)
+
+    def sum_i(self, *vals):
+        return self.reduce(list(vals), self.dist.ReduceOp.SUM, self.torch.int64)
+
+
+def measured_tensor_peaks(ctx):
+    """cuBLAS GEMM rates of THIS GPU for the two tensor-core number formats the dense kernels use (fp64 DMMA and
+    tf32): the denominators of the tensor rooflines.  MEASURED_PEAKS.json only holds a bf16 figure, which applies to
+    neither; best of 5 runs of a 6144^3 (fp64) / 8192^3 (tf32) torch.matmul, CUDA events."""
+    torch = ctx.torch
+    out = {}
+    old = torch.backends.cuda.matmul.allow_tf32
+    try:
+        for name, dt, n, tf32 in (("fp64_tflops", torch.float64, 6144, False), ("tf32_tflops", torch.float32, 8192, True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            a = torch.randn(n, n, device=ctx.dev, dtype=dt)
+            b = torch.randn(n, n, device=ctx.dev, dtype=dt)
+            torch.matmul(a, b)
+            best = 1e30
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                torch.matmul(a, b)
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            out[name] = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+            del a, b
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    torch.cuda.empty_cache()
+    return out
+
+
+def ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the workload's sampler kernel, from the committed
+    ncu --set full capture (profiles/traffic.json: written by tools/ncu_summary.py from the .ncu-rep, with the file
+    it came from).  None when no capture of this workload is committed."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        t = json.load(f).get(name)
+    if not t:
+        return None, None
+    return t["dram_bytes"], t["source"]
+
+
+def measure_device(ctx, name, w, steps, warmup, n=None, host_init=False, clocks=None):
+    """Device-timed run of one workload: `steps` launches of the fused sampler kernel (each `iters` sampling
+    iterations over the cloud), L2 flushed between steps, CUDA events, max over ranks."""
+    torch = ctx.torch
+    n = n or w["n"]
+    sampler, dist, X0, V0 = make_sampler(w, ctx.rank, n=n, device_init=None if host_init else ctx.dev)
     eng = sampler._engine
     iters = w["iters"]
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
-
-    def step():
-        return sampler.sample_device(iters)
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
+    for _ in range(warmup):
+        sampler.sample_device(iters)
+    ctx.barrier()
+    if clocks is not None:
         clocks.start()
     g0, x0, launches0 = dist.dEdX_count, sampler.grad_evals_executed, eng.launches
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    ctx.barrier()
     eng.kernel_events = []                    # CUDA events right around each sampler-kernel launch (roofline)
     t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.fill_(float(k))                 # evict the state from L2 between timed steps
+    for k in range(steps):
+        ctx.flush.fill_(float(k))             # evict the state from L2 between timed steps
         ev[k][0].record()
-        out = step()
+        out = sampler.sample_device(iters)
         ev[k][1].record()
         del out
-    barrier()
+    ctx.barrier()
     t_wall = time.perf_counter() - t_wall0
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop() if clocks is not None else None
     ms = sum(a.elapsed_time(b) for a, b in ev)
     kernel_ms = [a.elapsed_time(b) for a, b in eng.kernel_events]
     eng.kernel_events = None
     grads = sampler.grad_evals_executed - x0          # leapfrog steps actually integrated on the device
     grads_ref = dist.dEdX_count - g0                  # the reference's dEdX_count accounting
     launches = eng.launches - launches0
-    tt = torch.tensor([ms], dtype=torch.float64, device=dev)
-    gg = torch.tensor([grads, launches, grads_ref], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist_pkg.all_reduce(tt, op=dist_pkg.ReduceOp.MAX)
-        dist_pkg.all_reduce(gg, op=dist_pkg.ReduceOp.SUM)          # counters: the only cross-GPU reduction
-    ms_max = float(tt.item())
-    grads_all, launches_all, grads_ref_all = int(gg[0].item()), int(gg[1].item()), int(gg[2].item())
-    value = grads_all / (ms_max * 1e-3)
+    ms_max, launch_ms = ctx.max_f(ms, float(np.mean(kernel_ms)) if kernel_ms else ms / steps)
+    grads_all, launches_all, grads_ref_all = [int(v) for v in ctx.sum_i(grads, launches, grads_ref)]
+    return dict(name=name, w=w, n=n, sampler=sampler, dist=dist, X0=X0, V0=V0, steps=steps, warmup=warmup,
+                ms_max=ms_max, launch_ms=launch_ms, grads_all=grads_all, launches_all=launches_all,
+                grads_ref_all=grads_ref_all, value=grads_all / (ms_max * 1e-3), clk=clk, t_wall=t_wall)
 
-    # ---- ESS/s (BASELINE metric iii): T recorded steps, per-GPU autocorrelation sums, one all-reduce of float64[n_lags]
-    ess = None
-    if w.get("ess"):
-        from mjhmc_b200 import parallel
-        n_lags = w["ess"]["n_lags"]
-        barrier()
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        e0.record()
-        S = sampler.sample_device(iters)
-        e1.record()
-        part = parallel.autocorr_partial(S, n_lags=n_lags, circular=True)
-        if world > 1:
-            dist_pkg.all_reduce(part)                                   # the statistics "gathered over NVLink"
-        e2.record()
-        barrier()
-        ac = part.double().cpu().numpy()
-        ac = ac / ac[0]
-        ts = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist_pkg.all_reduce(ts, op=dist_pkg.ReduceOp.MAX)
-        ess_chain = _ess_from_curve(ac, iters)
-        total_s = float(ts.sum().item()) * 1e-3
-        ess = {"definition": "T / (1 + 2 sum_{tau>=1}^{first rho<0} rho_tau) on the circular fft_autocor curve (autocor.py:37-49), "
-                             "first %d lags" % n_lags,
-               "T": iters, "n_lags": n_lags, "chains": w["n"] * world, "ess_per_chain": ess_chain,
-               "sampling_ms": float(ts[0].item()), "autocorr_allreduce_ms": float(ts[1].item()),
-               "ess_per_s": ess_chain * w["n"] * world / total_s, "rho_1": float(ac[1]), "rho_last": float(ac[-1])}
-        del S, part
-        if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            ess["cpu"] = run_reference_ess(w)
 
-    # ---- e2e: host buffers in, host samples out, through the public API, every step
+def roofline_of(ctx, m, peaks):
+    """The roofline object of one measured workload."""
+    w, name, world = m["w"], m["name"], ctx.world
+    peak, peak_src = measured_peak()
+    ww = dict(w, n=m["n"])
+    alg = algorithmic_bytes_per_launch(ww)
+    launch_ms = m["launch_ms"]
+    achieved = alg / (launch_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(name)
+    if w["dist"] in ("GaussianRot", "ProductOfT"):
+        # dense-contraction energies: algorithmic flops per leapfrog step = 2 d^2 (S x) resp. 4 d nb (W^T x, W G)
+        fl = (2 if w["dist"] == "GaussianRot" else 4) * w["ndims"] ** 2
+        tf = m["grads_all"] * fl / (m["ms_max"] * 1e-3) / 1e12 / world
+        f32 = w.get("dtype") == "float32"
+        if f32:
+            tpeak = peaks.get("tf32_tflops", 1100.0) / 3.0
+            src = ("cuBLAS tf32 GEMM measured in this run (%.0f TFLOP/s) divided by the 3 MMAs of the 3xTF32 split"
+                   % peaks["tf32_tflops"]) if "tf32_tflops" in peaks else "nominal 1.1 PFLOP/s tf32 / 3"
+        else:
+            tpeak = peaks.get("fp64_tflops", 40.0)
+            src = ("cuBLAS fp64 GEMM (DMMA) measured in this run" if "fp64_tflops" in peaks
+                   else "nominal B200 fp64 tensor rate")
+        return {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": ("dense_tf32_kernel / pot_tf32_kernel (tcgen05.mma kind::tf32, 3 MMAs per product)" if f32
+                           else "dense_sample_kernel (mma.sync m8n8k4 f64 = DMMA)"),
+                "peak_source": src, "algorithmic_flops_per_leapfrog_step": fl, "launch_ms": launch_ms,
+                "hbm_gbs": achieved}
+    streaming = w.get("kernel") == "stream" or w["ndims"] > 16
+    if w["L"] <= 4:
+        note = "HBM-bound point"
+    elif streaming:
+        note = "L=%d leapfrog steps per sample through the streaming kernel (DESIGN.md 3.1b)" % w["L"]
+    else:
+        note = "L=%d leapfrog steps per sample: instruction-issue bound, not HBM bound (DESIGN.md 3.1)" % w["L"]
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "kernel": "stream_sample_kernel" if streaming else "fused_sample_kernel",
+                "algorithmic_bytes_per_launch": alg, "launch_ms": launch_ms, "note": note}
+    if w["dist"] == "RoughWell" and not streaming and w["L"] > 4:
+        # the pipe that does bound this kernel: fp64 instructions of the leapfrog loop per particle-dimension-step
+        # (3 FMAs for the two half kicks and the drift, 15 for x/s1^2 - c sin(2 pi x / s2): dists.cuh)
+        clk = m.get("clk")
+        fp64_inst = 18.0 * w["ndims"] * m["grads_all"] / world / (m["ms_max"] * 1e-3)
+        fp64_peak = 148 * 64 * ((clk or {}).get("sm_mhz") or 1965.0) * 1e6
+        roofline["fp64_pipe"] = {"achieved_inst_per_s": fp64_inst, "peak_inst_per_s": fp64_peak,
+                                 "frac": fp64_inst / fp64_peak,
+                                 "note": "algorithmic fp64 instructions of the leapfrog loop only; 64 fp64 lanes per SM at "
+                                         "the sampled SM clock (nominal issue rate: MEASURED_PEAKS.json has no fp64 figure)"}
+    return roofline
+
+
+def measure_ess(ctx, m, cpu=False):
+    """ESS/s (BASELINE metric iii): T recorded steps, per-GPU autocorrelation sums, one all-reduce of float64[n_lags]."""
+    torch = ctx.torch
+    from mjhmc_b200 import parallel
+    w, sampler = m["w"], m["sampler"]
+    iters, n_lags = w["iters"], w["ess"]["n_lags"]
+    ctx.barrier()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    S = sampler.sample_device(iters)
+    e1.record()
+    part = parallel.autocorr_partial(S, n_lags=n_lags, circular=True)
+    if ctx.world > 1:
+        ctx.dist.all_reduce(part)                                   # the statistics "gathered over NVLink"
+    e2.record()
+    ctx.barrier()
+    ac = part.double().cpu().numpy()
+    ac = ac / ac[0]
+    t_s, t_a = ctx.max_f(e0.elapsed_time(e1), e1.elapsed_time(e2))
+    ess_chain = _ess_from_curve(ac, iters)
+    crossed = bool(np.any(ac[1:] < 0))
+    ess = {"definition": "T / (1 + 2 sum_{tau>=1}^{first rho<0} rho_tau) on the circular fft_autocor curve (autocor.py:37-49), "
+                         "first %d lags" % n_lags,
+           "T": iters, "n_lags": n_lags, "chains": m["n"] * ctx.world, "ess_per_chain": ess_chain,
+           "sampling_ms": t_s, "autocorr_allreduce_ms": t_a, "autocorr_share_of_sampling": t_a / t_s,
+           "ess_per_s": ess_chain * m["n"] * ctx.world / ((t_s + t_a) * 1e-3), "rho_1": float(ac[1]),
+           "rho_last": float(ac[-1]), "rho_crosses_zero_inside_window": crossed,
+           "first_negative_lag": int(np.argmax(ac < 0)) if crossed else None}
+    del S, part
+    if cpu:
+        ess["cpu"] = run_reference_ess(w)
+    return ess
+
+
+def measure_pcie(ctx, nbytes=256 << 20):
+    """Plain device -> pinned host copy rate of this box, all ranks at once (the roof the e2e number sits on)."""
+    torch = ctx.torch
+    src = torch.empty(nbytes, dtype=torch.uint8, device=ctx.dev)
+    dst = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    dst.copy_(src, non_blocking=True)
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        dst.copy_(src, non_blocking=True)
+    ctx.barrier()
+    t = ctx.max_f(time.perf_counter() - t0)[0]
+    return 4 * nbytes * ctx.world / t / 1e9
+
+
+def measure_e2e(ctx, m, steps):
+    """The same work through the public API with HOST buffers: state uploaded from pinned host memory, sample()
+    returns a host numpy array, every step."""
+    torch = ctx.torch
     from mjhmc_b200.samplers.hmc_state import HMCState
-    Xh = torch.as_tensor(X0).pin_memory()                  # host inputs live in pinned memory
-    Vh = torch.as_tensor(V0).pin_memory()
-    e2e_steps = max(1, min(args.steps, 5))
-
-    e2e_iters = 8 if w.get("ess") else iters                 # the ESS workload records 256 steps on the device only
+    w, sampler = m["w"], m["sampler"]
+    Xh = torch.as_tensor(m["X0"]).pin_memory()                  # host inputs live in pinned memory
+    Vh = torch.as_tensor(m["V0"]).pin_memory()
+    e2e_steps = max(1, min(steps, 5))
+    e2e_iters = 8 if w.get("ess") else w["iters"]
 
     def e2e_step():
         sampler.state = HMCState.from_buffers(sampler, Xh, Vh)   # H2D from pinned memory at the next launch
-        return sampler.sample(e2e_iters)                     # D2H of (ndims, iters * n)
+        return sampler.sample(e2e_iters)                         # D2H of (ndims, iters * n)
 
-    for _ in range(2):                                       # warm the pinned staging buffers (not timed)
+    for _ in range(2):                                           # warm the pinned staging buffers (not timed)
         res = e2e_step()
-    barrier()
+    ctx.barrier()
     g1 = sampler.grad_evals_executed
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         res = e2e_step()
-    barrier()
-    e2e_t = time.perf_counter() - t0
-    ee = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
-    ge = torch.tensor([sampler.grad_evals_executed - g1], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist_pkg.all_reduce(ee, op=dist_pkg.ReduceOp.MAX)
-        dist_pkg.all_reduce(ge, op=dist_pkg.ReduceOp.SUM)
-    e2e_value = int(ge.item()) / float(ee.item())
+    ctx.barrier()
+    e2e_t = ctx.max_f(time.perf_counter() - t0)[0]
+    ge = ctx.sum_i(sampler.grad_evals_executed - g1)[0]
     S = 4 if w.get("dtype") == "float32" else 8
-    h2d = 2 * w["ndims"] * w["n"] * S + w["n"] * (S + 1)
+    h2d = 2 * w["ndims"] * m["n"] * S + m["n"] * (S + 1)
     d2h = res.nbytes
+    pcie = measure_pcie(ctx)
+    copy_s = e2e_steps * (h2d + d2h) * ctx.world / (pcie * 1e9)
+    return {"value": int(ge) / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "steps": e2e_steps, "iterations_per_step": e2e_iters,
+            "pcie_gbs": pcie, "pcie_note": "plain device->pinned-host copies of 256 MB, all %d ranks at once, same run" % ctx.world,
+            "copy_time_share": copy_s / e2e_t,
+            "roof_value": int(ge) / copy_s if copy_s > 0 else None}
+
+
+# the workloads whose device-timed value + roofline ride along in the default line (BASELINE configs 2-5 and the two
+# north_star targets: >= 0.8 of the HBM roofline on fused Gaussian / RoughWell leapfrog, >= 50 % tensor pipe on PoT)
+SECONDARY = ["roughwell2d_control", "gauss10d_control_L1_stream", "gauss100d_diag_control_L1",
+             "testgauss2d_control_L1_stream", "roughwell2d_control_L1_stream", "roughwell10d_control_L1_stream",
+             "gauss100d_diag_mjhmc", "gauss100d_mjhmc", "gauss100d_mjhmc_f32", "pot100d_mjhmc", "pot100d_mjhmc_f32",
+             "funnel10d_cthmc", "funnel10d_cthmc_ess"]
+
+
+def summarise(ctx, m, peaks):
+    w = m["w"]
+    return {"value": m["value"], "unit": UNIT, "ms_per_step": m["ms_max"] / m["steps"], "steps": m["steps"],
+            "warmup": m["warmup"], "dtype": "f32" if w.get("dtype") == "float32" else "f64",
+            "particles_per_gpu": m["n"], "iterations_per_step": w["iters"], "sampler": w["sampler"],
+            "hyper_parameters": {"epsilon": w["epsilon"], "beta": w["beta"], "L": w["L"], "source": w["source"]},
+            "gpu_launches": m["launches_all"], "roofline": roofline_of(ctx, m, peaks),
+            "particle_iterations_per_s": m["n"] * ctx.world * w["iters"] * m["steps"] / (m["ms_max"] * 1e-3)}
+
+
+def run_b200(args, w):
+    ctx = Ctx()
+    torch = ctx.torch
+    rank, world = ctx.rank, ctx.world
+    strong = args.scaling == "strong"
+    n_main = w["n"] // world if strong else w["n"]
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = run_reference(w, steps=2, warmup=1)
+
+    peaks = measured_tensor_peaks(ctx)
+    clocks = ClockSampler(ctx.local_rank) if rank == 0 else None
+    m = measure_device(ctx, args.workload, w, args.steps, args.warmup, n=n_main, host_init=True, clocks=clocks)
+    ess = measure_ess(ctx, m, cpu=(rank == 0 and world == 1 and not args.no_cpu_baseline)) if w.get("ess") else None
+    e2e = measure_e2e(ctx, m, args.steps)
+    main_summary = summarise(ctx, m, peaks)
+    clk = m["clk"]
+
+    # ---- strong scaling of the same workload (the cloud of ONE GPU's worth split over the ranks), N > 1 only
+    strong_line = None
+    if world > 1 and not strong and not args.no_secondary:
+        for key in ("sampler", "dist", "X0", "V0"):
+            m.pop(key, None)
+        torch.cuda.empty_cache()
+        ms_ = measure_device(ctx, args.workload, w, args.steps, args.warmup, n=w["n"] // world)
+        strong_line = {"value": ms_["value"], "unit": UNIT, "particles_total": (w["n"] // world) * world,
+                       "particles_per_gpu": w["n"] // world, "ms_per_step": ms_["ms_max"] / ms_["steps"],
+                       "note": "strong scaling: the single-GPU cloud split over the %d ranks" % world}
+        del ms_
+
+    # ---- the other BASELINE configs and the north_star target points, device-timed (few steps each)
+    workloads = {}
+    if args.workload == DEFAULT_WORKLOAD and not strong and not args.no_secondary:
+        for key in ("sampler", "dist", "X0", "V0"):
+            m.pop(key, None)
+        for name in SECONDARY:
+            torch.cuda.empty_cache()
+            w2 = WORKLOADS[name]
+            try:
+                m2 = measure_device(ctx, name, w2, steps=5, warmup=3)
+                workloads[name] = summarise(ctx, m2, peaks)
+                if w2.get("ess"):
+                    workloads[name]["ess"] = measure_ess(ctx, m2)
+            except Exception as exc:   # noqa: BLE001 -- a secondary workload must not lose the headline line
+                workloads[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            m2 = None
 
     if rank == 0:
-        peak, peak_src = measured_peak()
-        alg = algorithmic_bytes_per_launch(w)
-        # roofline: the sampler kernel alone (a step also resets and reads back the counter block)
-        launch_ms = float(np.mean(kernel_ms)) if kernel_ms else ms_max / args.steps
-        achieved = alg / (launch_ms * 1e-3) / 1e9
-        if w["dist"] in ("GaussianRot", "ProductOfT"):
-            # dense-contraction energies: algorithmic flops per leapfrog step = 2 d^2 (S x) resp. 4 d nb (W^T x, W G)
-            fl = (2 if w["dist"] == "GaussianRot" else 4) * w["ndims"] ** 2
-            tf = grads_all * fl / (ms_max * 1e-3) / 1e12 / world
-            f32 = w.get("dtype") == "float32"
-            tpeak = 1100.0 / 3.0 if f32 else 40.0
-            roofline = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
-                        "traffic": None,
-                        "kernel": "dense_tf32_kernel (tcgen05.mma kind::tf32, 3 MMAs per product)" if f32
-                                  else "dense_sample_kernel (mma.sync m8n8k4 f64 = DMMA)",
-                        "peak_source": ("nominal B200 dense tf32 rate 1.1 PFLOP/s divided by the 3 MMAs of the 3xTF32 split"
-                                        if f32 else
-                                        "nominal B200 fp64 tensor-core rate; MEASURED_PEAKS.json has no fp64 figure "
-                                        "(its bf16 cuBLAS number does not apply to an fp64 path)"),
-                        "algorithmic_flops_per_leapfrog_step": fl, "launch_ms": launch_ms,
-                        "hbm_gbs": achieved, "note": "ncu sm__pipe_tensor_cycles_active in profiles/r1_dense_*.txt"}
-        else:
-            streaming = w.get("kernel") == "stream" or w["ndims"] > 16
-            if w["L"] <= 4:
-                note = "HBM-bound point"
-            elif streaming:
-                note = ("L=%d leapfrog steps per sample through the streaming kernel: neither HBM- nor fp64-bound yet "
-                        "(DESIGN.md 3.1b)" % w["L"])
-            else:
-                note = ("L=%d leapfrog steps per sample: the kernel is FP64-issue bound "
-                        "(ncu sm__pipe_fp64_cycles_active 71%%, DESIGN.md 3.1), not HBM bound" % w["L"])
-            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": TRAFFIC.get(args.workload), "peak_source": peak_src,
-                        "kernel": "stream_sample_kernel" if streaming else "fused_sample_kernel",
-                        "algorithmic_bytes_per_launch": alg, "launch_ms": launch_ms, "note": note}
-            if w["dist"] == "RoughWell" and not streaming:
-                # the pipe that does bound this kernel: fp64 instructions of the leapfrog loop per particle-dimension-step
-                # (3 FMAs for the two half kicks and the drift, 15 for x/s1^2 - c sin(2 pi x / s2): dists.cuh)
-                fp64_inst = 18.0 * w["ndims"] * grads_all / world / (ms_max * 1e-3)
-                fp64_peak = 148 * 64 * (clk["sm_mhz"] or 1965.0) * 1e6 if clk else 148 * 64 * 1.965e9
-                roofline["fp64_pipe"] = {"achieved_inst_per_s": fp64_inst, "peak_inst_per_s": fp64_peak,
-                                         "frac": fp64_inst / fp64_peak,
-                                         "note": "algorithmic fp64 instructions of the leapfrog loop only; 64 fp64 lanes per SM "
-                                                 "and clock at the sampled SM clock; ncu sm__pipe_fp64_cycles_active = 71%"}
+        iters = w["iters"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if w.get("dtype") == "float32" else "f64", "data": "synthetic",
+            "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": m["ms_max"] / args.steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f32" if w.get("dtype") == "float32" else "f64", "data": "synthetic",
             "config": {"workload": "%s: %s %d-d, %d particles per GPU, %s eps=%g beta=%g L=%d (%s); %d sampling "
                                    "iterations per step in one fused launch" % (
-                                       args.workload, w["dist"], w["ndims"], w["n"], w["sampler"], w["epsilon"], w["beta"],
+                                       args.workload, w["dist"], w["ndims"], n_main, w["sampler"], w["epsilon"], w["beta"],
                                        w["L"], w["source"], iters),
-                       "particles_per_gpu": w["n"], "iterations_per_step": iters,
+                       "particles_per_gpu": n_main, "iterations_per_step": iters,
                        "l2": "flushed with a 256 MB fill between timed steps", "rng": "philox4x32-10",
                        "parallelism": "particle shards, dp%d" % world},
-            "roofline": roofline,
+            "roofline": main_summary["roofline"],
             "cpu_baseline": cpu_baseline,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "iterations_per_step": e2e_iters},
-            "gpu_launches": launches_all,
+            "e2e": e2e,
+            "gpu_launches": m["launches_all"],
             "ess": ess,
             "clocks": clk,
-            "wall_s_timed_region": t_wall,
-            "grad_evals_executed": grads_all,
-            "dEdX_count_delta": grads_ref_all,
-            "dEdX_count_rate": grads_ref_all / (ms_max * 1e-3),
-            "particle_iterations_per_s": w["n"] * world * iters * args.steps / (ms_max * 1e-3),
+            "measured_tensor_peaks": peaks,
+            "wall_s_timed_region": m["t_wall"],
+            "grad_evals_executed": m["grads_all"],
+            "dEdX_count_delta": m["grads_ref_all"],
+            "dEdX_count_rate": m["grads_ref_all"] / (m["ms_max"] * 1e-3),
+            "particle_iterations_per_s": n_main * world * iters * args.steps / (m["ms_max"] * 1e-3),
         }
+        if strong_line:
+            line["strong_scaling"] = strong_line
+        if workloads:
+            line["workloads"] = workloads
         print(json.dumps(line))
     if world > 1:
-        dist_pkg.destroy_process_group()
+        ctx.dist.destroy_process_group()
 
 
 def main():
@@ -550,6 +745,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads / strong-scaling leg")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: the workload's particle count is the TOTAL, split over the ranks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     w = WORKLOADS[args.workload]
