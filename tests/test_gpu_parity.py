@@ -2,7 +2,7 @@
 and against the oracle on the same injected draws.
 
 Tolerances (north_star): trajectories 1e-10 relative in fp64, 1e-4 relative in fp32, per element
-(helpers.rel_err: every value against its own magnitude, floored at 1e-2 (fp64) / 1e-1 (fp32) of the array's RMS); integer counters
+(helpers.rel_err: every value against its own magnitude, floored at one tenth of the array's RMS); integer counters
 and operator choices exact.
 """
 import numpy as np
