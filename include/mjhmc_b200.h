@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MJHMC_ABI_VERSION 1
+#define MJHMC_ABI_VERSION 2
 
 /* dtype of the state arrays X, V, samples, H cache (arithmetic type of the path) */
 enum { MJHMC_F32 = 0, MJHMC_F64 = 1 };
@@ -41,8 +41,9 @@ enum {
     MJHMC_DIST_FUNNEL         = 3, /* tf_distributions.py:143-147 (Neal's funnel)  p[0]=scale        */
     MJHMC_DIST_FUNNEL_LITERAL = 4, /* tf_distributions.py:158-165 as written        p[0]=scale        */
     MJHMC_DIST_DENSE_GAUSSIAN = 5, /* distributions.py:268-273 full J; a0 = (J+J^T)/2 [ndims x ndims];
-                                      fp32 only: a1 = workspace filled by mjhmc_dense_tf32_prepare */
-    MJHMC_DIST_PRODUCT_OF_T   = 6, /* distributions.py:420-433; a0=W [ndims x nbasis], a1=nu, a2=b    */
+                                      fp32: ws = workspace filled by mjhmc_dense_tc_prepare */
+    MJHMC_DIST_PRODUCT_OF_T   = 6, /* distributions.py:420-433; a0=W [ndims x nbasis], a1=nu, a2=b;
+                                      fp32: ws = workspace filled by mjhmc_dense_tc_prepare */
     MJHMC_DIST_MULTIMODAL     = 7  /* distributions.py:314-335  two Gaussians at -/+ 2*separation along dim 0; p[0]=separation */
 };
 
@@ -76,6 +77,8 @@ typedef struct mjhmc_dist {
     int32_t nbasis;     /* ProductOfT only */
     double  p[4];       /* scalar parameters, see MJHMC_DIST_* */
     const void *a0, *a1, *a2;   /* device parameter arrays, see MJHMC_DIST_* */
+    const void *ws;             /* fp32 DENSE_GAUSSIAN / PRODUCT_OF_T: caller-owned device workspace of
+                                   mjhmc_dense_tc_workspace_bytes(dist) bytes, filled once by mjhmc_dense_tc_prepare */
 } mjhmc_dist;
 
 /* hyper-parameters after the host-side derivation of markov_jump_hmc.py:67-80,189,197-200,221-223 */
@@ -201,11 +204,13 @@ int mjhmc_transition(int32_t dtype, int32_t ndims, const mjhmc_hp *hp, const mjh
                      const void *H_flf, void *H_cache, uint8_t *cache_active,
                      const mjhmc_outputs *o, void *stream);
 
-/* fp32 full-covariance Gaussian on the tcgen05 tensor cores: the kernel consumes the matrix pre-tiled into
- * K-major 8x16-byte core matrices and split into tf32 hi / lo parts.  The caller allocates
- * mjhmc_dense_tf32_workspace_bytes(ndims) bytes, points dist->a1 at them and calls prepare once. */
-int64_t mjhmc_dense_tf32_workspace_bytes(int32_t ndims);
-int mjhmc_dense_tf32_prepare(const mjhmc_dist *dist, void *stream);
+/* fp32 dense-contraction energies on the tcgen05 tensor cores (replaces the np.dot / Theano contractions of
+ * distributions.py:268-273 and :420-433 for fp32 states): the kernel consumes the matrix (S, or W of ProductOfT)
+ * pre-tiled into 8-row x 16-byte core matrices and split into three bf16 planes (+ the per-expert tables of
+ * ProductOfT).  The caller allocates mjhmc_dense_tc_workspace_bytes(dist) bytes, points dist->ws at them and calls
+ * prepare once per distribution; sampler launches only read the workspace. */
+int64_t mjhmc_dense_tc_workspace_bytes(const mjhmc_dist *dist);
+int mjhmc_dense_tc_prepare(const mjhmc_dist *dist, void *stream);
 
 /* Folds the striped counter rows into host int64[MJHMC_N_COUNTERS] (synchronises the stream). */
 int mjhmc_counters_read(const int64_t *counters, int64_t *out_host, void *stream);

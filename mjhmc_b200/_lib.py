@@ -20,12 +20,13 @@ N_COUNTERS = 8
 COUNTER_STRIPES = 32
 COUNTER_ROWS = COUNTER_STRIPES + 1
 INT64_MAX = (1 << 63) - 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class Dist(C.Structure):
     _fields_ = [("kind", C.c_int32), ("dtype", C.c_int32), ("ndims", C.c_int32), ("nbasis", C.c_int32),
-                ("p", C.c_double * 4), ("a0", C.c_void_p), ("a1", C.c_void_p), ("a2", C.c_void_p)]
+                ("p", C.c_double * 4), ("a0", C.c_void_p), ("a1", C.c_void_p), ("a2", C.c_void_p),
+                ("ws", C.c_void_p)]
 
 
 class HP(C.Structure):
@@ -77,8 +78,8 @@ SYMBOLS = {
                              C.c_void_p]),
     "mjhmc_transition": (C.c_int, [C.c_int32, C.c_int32, _P(HP), _P(RNG), C.c_int64, C.c_int64, _P(FullState),
                                    _P(FullState), C.c_void_p, C.c_void_p, C.c_void_p, _P(Outputs), C.c_void_p]),
-    "mjhmc_dense_tf32_workspace_bytes": (C.c_int64, [C.c_int32]),
-    "mjhmc_dense_tf32_prepare": (C.c_int, [_P(Dist), C.c_void_p]),
+    "mjhmc_dense_tc_workspace_bytes": (C.c_int64, [_P(Dist)]),
+    "mjhmc_dense_tc_prepare": (C.c_int, [_P(Dist), C.c_void_p]),
     "mjhmc_counters_read": (C.c_int, [C.c_void_p, _P(C.c_int64), C.c_void_p]),
     "mjhmc_counters_reset": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mjhmc_resample_scratch_bytes": (C.c_int64, [C.c_int64]),

@@ -91,7 +91,7 @@ static int fill_dist(LaunchParams& p, const mjhmc_dist* dist) {
     p.d = dist->ndims;
     p.nbasis = dist->nbasis;
     for (int k = 0; k < 4; ++k) p.dp[k] = dist->p[k];
-    p.a0 = dist->a0; p.a1 = dist->a1; p.a2 = dist->a2;
+    p.a0 = dist->a0; p.a1 = dist->a1; p.a2 = dist->a2; p.ws = dist->ws;
     if (dist->kind == MJHMC_DIST_ROUGH_WELL) fill_roughwell_coef(p.coef, dist->dtype, dist->p[1]);
     return 0;
 }
@@ -289,13 +289,19 @@ int mjhmc_counters_read(const int64_t* counters, int64_t* out_host, void* stream
     return 0;
 }
 
-int64_t mjhmc_dense_tf32_workspace_bytes(int32_t ndims) { return ndims > 0 ? dense_tf32_workspace_bytes(ndims) : -1; }
-
-int mjhmc_dense_tf32_prepare(const mjhmc_dist* dist, void* stream) {
+int64_t mjhmc_dense_tc_workspace_bytes(const mjhmc_dist* dist) {
     if (check_dist(dist)) return -1;
-    if (dist->kind != MJHMC_DIST_DENSE_GAUSSIAN || dist->dtype != MJHMC_F32) return fail("tf32 workspace is for the fp32 dense Gaussian");
-    if (!dist->a1) return fail("dist->a1 (workspace) is NULL");
-    return check(dense_tf32_prepare((const float*)dist->a0, dist->ndims, (float*)dist->a1, (cudaStream_t)stream), "tf32_prep_kernel");
+    if (dist->dtype != MJHMC_F32 || !dense_tc_supported(dist->kind, dist->ndims, dist->nbasis)) { fail("no tensor-core workspace for this distribution"); return -1; }
+    return dense_tc_workspace_bytes(dist->kind, dist->ndims);
+}
+
+int mjhmc_dense_tc_prepare(const mjhmc_dist* dist, void* stream) {
+    if (check_dist(dist)) return -1;
+    if (dist->dtype != MJHMC_F32 || !dense_tc_supported(dist->kind, dist->ndims, dist->nbasis))
+        return fail("the tensor-core workspace is for the fp32 dense Gaussian / ProductOfT (ndims <= 112)");
+    if (!dist->ws) return fail("dist->ws (workspace) is NULL");
+    return check(dense_tc_prepare(dist->kind, (const float*)dist->a0, (const float*)dist->a1, (const float*)dist->a2, dist->ndims,
+                                  (void*)dist->ws, (cudaStream_t)stream), "tc_prep_kernel");
 }
 
 int64_t mjhmc_resample_scratch_bytes(int64_t m) { return m < 0 ? -1 : resample_scratch_bytes(m); }

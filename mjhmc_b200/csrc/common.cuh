@@ -40,6 +40,7 @@ struct LaunchParams {
     double dp[4];
     double coef[12];                 // distribution-specific constants precomputed on the host (api.cu)
     const void* a0; const void* a1; const void* a2; int nbasis;
+    const void* ws;                  // fp32 dense kinds: the pre-tiled matrix planes (mjhmc_dense_tc_prepare)
 };
 
 // ---------------------------------------------------------------- Philox4x32-10

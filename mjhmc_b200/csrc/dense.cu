@@ -429,7 +429,7 @@ static int dense_mt(int d) {
 }
 
 bool dense_supported(int dtype, int kind, int ndims, int nbasis) {
-    if (dtype == MJHMC_F32) return dense_tf32_supported(kind, ndims);
+    if (dtype == MJHMC_F32) return dense_tc_supported(kind, ndims, nbasis);
     if (kind == MJHMC_DIST_PRODUCT_OF_T && nbasis != ndims) return false;
     const int mt = dense_mt(ndims);
     if (!mt) return false;
@@ -454,7 +454,7 @@ static cudaError_t launch_dense_T(const LaunchParams& p, cudaStream_t stream) {
 }
 
 cudaError_t launch_dense(int dtype, int kind, const LaunchParams& p, cudaStream_t stream) {
-    if (dtype == MJHMC_F32) return dense_tf32_supported(kind, p.d) ? launch_dense_tf32(p, stream) : cudaErrorNotSupported;
+    if (dtype == MJHMC_F32) return dense_tc_supported(kind, p.d, p.nbasis) ? launch_dense_tc(kind, p, stream) : cudaErrorNotSupported;
     const bool pot = kind == MJHMC_DIST_PRODUCT_OF_T;
     switch (dense_mt(p.d)) {
         case 4:  return pot ? launch_dense_T<4, true>(p, stream) : launch_dense_T<4, false>(p, stream);

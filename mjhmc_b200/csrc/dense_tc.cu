@@ -1,38 +1,47 @@
-// K4 (fp32 states): fused sampler for the full-covariance Gaussian on the 5th-generation tensor
-// cores -- tcgen05.mma kind::tf32 with the accumulator in TMEM, the matrix staged by a TMA bulk
-// copy, 3xTF32 operand splitting for fp32-grade gradients.
+// K4 (fp32 states): fused sampler for the dense-contraction energies on the 5th-generation tensor cores --
+// tcgen05.mma with the accumulators in TMEM, the matrix staged by one TMA bulk copy per CTA.
 //
-//   dEdX = S x,  E = x.(S x)/2,  S = (J + J^T)/2          misc/distributions.py:268-273
+//   full-covariance Gaussian  dEdX = S x, E = x.(S x)/2, S = (J + J^T)/2                 misc/distributions.py:268-273
+//   ProductOfT                Y = W^T x + b, E = sum_j (nu_j+1)/2 log(1 + (y_j/nu_j)^2),   misc/distributions.py:420-433
+//                             G_j = (nu_j+1) y_j / (nu_j^2 + y_j^2), dEdX = W G            (autodiff of :431)
 //
-// Mapping.  A CTA works on a tile of 128 particles with 4 threads per particle (512 threads): thread
-// (m, q) owns a quarter of the dims of particle m -- that slice of the momentum lives in its
-// registers, the position in the A-operand tile in shared memory.  (One thread per particle, the
-// first version, left one warp per scheduler and 90 % issue stalls: profiles/r1_dense_tc_v1.txt.)
-// The gradient of the whole tile is one accumulator
-//       D[128 particles x N dims] = Xtile[128 x K] . S^T[K x N]
-//   A = Xtile : K-major, no swizzle: 8-particle x 4-dim core matrices (16 bytes per particle row), the
-//       16 particle groups of one 4-dim core column contiguous (SBO = 128 B, LBO = 2 KB), so the 32
-//       lanes of a warp store 32 consecutive 16-byte rows -- conflict-free float4 stores
-//   B = S     : K-major, no swizzle (8 x 16-byte core matrices), pre-tiled in HBM by
-//       tf32_prep_kernel and brought in with ONE cp.async.bulk (TMA) per CTA
-//   D         : TMEM lane = particle, column = dim, so tcgen05.ld.32x32b hands every thread the
-//       gradient of its own particle; kick, drift and x.g are thread-local (no shuffles)
-// 3xTF32: x = x_hi + x_lo, S = S_hi + S_lo with *_hi carrying the top 10 mantissa bits;
-//   D = x_hi S_hi + x_lo S_hi + x_hi S_lo  (three MMAs per 8-wide K step) is accurate to ~2^-21.
-// One elected thread issues the MMAs; completion reaches the CTA through tcgen05.commit -> mbarrier.
+// Rows are JOBS.  A tile is 128 independent trajectories: the L trajectory of every particle of a chunk and, packed
+// behind them, the F.L.F trajectories of only those particles whose cached FLF energy is not valid
+// (hmc_state.py:109-119).  Round 1 ran the FLF pass for a whole tile whenever one of its 128 particles needed it --
+// twice the work for ~1.1x the trajectories.  Persistent CTAs own contiguous particle ranges and cut them into
+// chunks of P particles with P + #FLF(P) <= 128.
+//
+// Arithmetic: fp32 operands are split into three bf16 planes (x = x0 + x1 + x2, 8 + 8 + 8 mantissa bits; the
+// split is exact) and a product is the six MMAs x0w0 + x0w1 + x1w0 + x1w1 + x0w2 + x2w0 of kind::f16 (bf16 in,
+// fp32 accumulate): the dropped terms are below 2^-24.  bf16 -- not tf32 as in round 1 -- because ProductOfT needs
+// W in BOTH orientations (Y = X W contracts over dims, dEdX = G W^T over experts): one no-swizzle buffer of
+// 8 x 16-byte core matrices can be described K-major (N = dim, K = expert) and MN-major (N = expert, K = dim) at
+// once, and the tensor core honours the MN-major view for 16-bit operands but returns zeros for tf32
+// (tools/probe/tc_probe2.cu / tc_probe3.cu on the GPU box).  Two tf32 copies of a 100 x 100 W (hi + lo each) do not
+// fit beside the particle tile in 227 KB; three bf16 planes of ONE copy do (75 KB), at the same MMA cycle count.
+//
+// Pipeline inside a tile.  16 epilogue warps (4 threads per row: thread (m, q) owns the 8-wide core columns
+// q, 4+q, 8+q, 12+q of row m -- positions and momenta of those dims stay in its registers) and one MMA warp.
+// A product is cut into K chunks of 32 columns.  The epilogue threads write chunk c of the next A operand
+// (positions after the drift, or G for ProductOfT), fence, and arrive on bar_chunk[c]; the MMA warp waits for
+// chunk c only and issues its 12 MMAs while the epilogue threads work on chunk c+1; after the last chunk it commits
+// to bar_done.  The accumulator is double-buffered in TMEM (the Gaussian alternates D0 / D1, ProductOfT keeps Y in
+// D0 and dEdX in D1), so the MMAs of product n+1 may overwrite nothing the epilogue of product n still reads.
+// Round 1's kernel was MMA -> epilogue -> MMA strictly serial (tensor pipe 29.7 % active).
+#include <cuda_bf16.h>
 #include "dense.h"
 
 namespace mjhmc {
 
-constexpr int kTcTile = 128;                   // particles per tile (M of the MMA)
-constexpr int kTcSplit = 4;                    // threads per particle: each owns a quarter of the dims
-constexpr int kTcThreads = kTcTile * kTcSplit; // 16 warps: warp w reads TMEM lanes 32 (w % 4) ..
-constexpr int kTcMaxDim = 104;                 // padded dims (N and K of the MMA)
-constexpr int kTcMaxCores = kTcMaxDim / 4;     // 4-dim core columns of the A tile
-constexpr int kTcCoresPerThread = (kTcMaxCores + kTcSplit - 1) / kTcSplit;   // 7
-constexpr int kTcDimsPerThread = kTcCoresPerThread * 4;                      // 28
-constexpr int kTcTmemCols = 128;
-constexpr int kTcCoreColBytes = 2048;          // one 4-dim core column of the A tile: 16 particle groups x 128 B
+constexpr int kTcRows = 128;                       // job rows per tile (M of the MMA)
+constexpr int kTcSplit = 4;                        // epilogue threads per row
+constexpr int kTcEpiThreads = kTcRows * kTcSplit;  // 16 warps; warp w reads TMEM lanes 32 (w % 4) ..
+constexpr int kTcThreads = kTcEpiThreads + 32;     // + the MMA-issuing warp
+constexpr int kTcMaxP = 112;                       // padded dims / experts (K and N of the MMAs), a multiple of 16
+constexpr int kTcCPT = 4;                          // 8-wide core columns per thread (and K chunks per product)
+constexpr int kTcCoreColBytes = 2048;              // one 8-wide core column of an A plane: 16 row groups x 128 B
+constexpr int kTcTmemCols = 256;                   // two accumulators of 128 columns
+constexpr int kTcTabs = 5;                         // ProductOfT per-expert tables: nu+1, nu^2, b, (nu+1)/2, 1/nu^2
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -41,6 +50,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -68,22 +80,22 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// 8 consecutive accumulator columns of this thread's TMEM lane
+// 8 consecutive accumulator columns of this thread's TMEM lane.  Load and wait in ONE asm statement: the registers
+// are only defined after tcgen05.wait::ld, and a separate wait statement would not stop the compiler from consuming
+// them earlier.
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
     uint32_t u[8];
-    // load and wait in ONE asm statement: the registers are only defined after tcgen05.wait::ld, and a
-    // separate wait statement would not stop the compiler from consuming them earlier
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
                  "tcgen05.wait::ld.sync.aligned;"
                  : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
@@ -92,85 +104,112 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
     for (int j = 0; j < 8; ++j) r[j] = __uint_as_float(u[j]);
 }
 
-// 32 consecutive accumulator columns of this thread's TMEM lane (load + wait in one statement)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&r)[32]) {
-    uint32_t u[32];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
-                 "tcgen05.wait::ld.sync.aligned;"
-                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-                 : "r"(taddr) : "memory");
-#pragma unroll
-    for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(u[j]);
-}
-
-// shared-memory matrix descriptors (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+// shared-memory matrix descriptor, no swizzle (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((addr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
-    d |= (uint64_t)layout_type << 61;              // 0 = no swizzle, 2 = SWIZZLE_128B
     return d;
 }
 
-// top 19 bits (sign, exponent, 10 mantissa bits): exactly what the tf32 datapath reads
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-
-// byte offset of the 4-dim row of particle m in core column kc (dims 4kc..4kc+3) of an A tile
+// byte offset of the 16-byte row (8 bf16) of job row m in core column kc (columns 8kc .. 8kc+7) of an A plane:
+// K-major, 8-row x 16-byte core matrices, the 16 row groups of one core column contiguous (SBO = 128, LBO = 2048),
+// so the 32 lanes of a warp store 32 consecutive 16-byte rows -- conflict-free 128-bit stores.
 __device__ __forceinline__ uint32_t a_row_offset(int m, int kc) {
     return (uint32_t)kc * kTcCoreColBytes + (uint32_t)(m >> 3) * 128u + (uint32_t)(m & 7) * 16u;
 }
 
-// Pre-tile S (fp32, d x d row-major) into the K-major core-matrix layout, split into hi / lo.
-// out: [hi block | lo block], each ngroups * kcores * 32 floats; element (n, k) at
-//      (n/8)*(kcores*32) + (k/4)*32 + (n%8)*4 + (k%4)
-__global__ void tf32_prep_kernel(const float* __restrict__ S, int d, int ngroups, int kcores, float* __restrict__ out) {
-    const int total = ngroups * 8 * kcores * 4;
-    const int block = ngroups * kcores * 32;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int n = idx / (kcores * 4), k = idx - n * (kcores * 4);
-        const float val = (n < d && k < d) ? S[n * d + k] : 0.0f;
-        const float hi = tf32_hi(val);
-        const int off = (n >> 3) * (kcores * 32) + (k >> 2) * 32 + (n & 7) * 4 + (k & 3);
-        out[off] = hi;
-        out[block + off] = val - hi;
+// x = x0 + x1 + x2 with bf16 parts (round to nearest; the remainders are exact): 8 values -> one 16-byte row per plane
+__device__ __forceinline__ void split3_store(const float (&x)[8], uint8_t* plane0, uint32_t plane_bytes, uint32_t off) {
+    uint32_t p0[4], p1[4], p2[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const float a = x[2 * jj], b = x[2 * jj + 1];
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(a, b);                 // .x = a: low half = lower address
+        const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0);
+        const float ra = a - __uint_as_float(u0 << 16), rb = b - __uint_as_float(u0 & 0xFFFF0000u);
+        const __nv_bfloat162 h1 = __floats2bfloat162_rn(ra, rb);
+        const uint32_t u1 = *reinterpret_cast<const uint32_t*>(&h1);
+        const float sa = ra - __uint_as_float(u1 << 16), sb = rb - __uint_as_float(u1 & 0xFFFF0000u);
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(sa, sb);
+        p0[jj] = u0; p1[jj] = u1; p2[jj] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(plane0 + off) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+    *reinterpret_cast<uint4*>(plane0 + plane_bytes + off) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+    *reinterpret_cast<uint4*>(plane0 + 2u * plane_bytes + off) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+}
+
+// Pre-tile the matrix (fp32, rows x cols row-major) into three bf16 planes of 8-row x 16-byte core matrices:
+// element (r, c) at (r/8)*(nc*128) + (c/8)*128 + (r%8)*16 + (c%8)*2 bytes of its plane, nc = P/8.
+// Gaussian: M = S.  ProductOfT: M = W[dim][expert]; the per-expert tables follow the planes.
+__global__ void tc_prep_kernel(const float* __restrict__ Mx, int rows, int cols, int P, const float* __restrict__ nu,
+                               const float* __restrict__ b, uint8_t* __restrict__ out) {
+    const int nc = P >> 3;
+    const uint32_t plane = (uint32_t)nc * nc * 128u;
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P * P; idx += gridDim.x * blockDim.x) {
+        const int r = idx / P, c = idx - r * P;
+        const float val = (r < rows && c < cols) ? Mx[r * cols + c] : 0.0f;
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(val);
+        const float r1 = val - __bfloat162float(h0);
+        const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+        const __nv_bfloat16 h2 = __float2bfloat16_rn(r1 - __bfloat162float(h1));
+        const uint32_t off = ((uint32_t)(r >> 3) * (nc * 128u) + (uint32_t)(c >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(c & 7) * 2u) >> 1;
+        o[off] = h0;
+        o[(plane >> 1) + off] = h1;
+        o[plane + off] = h2;                       // 2 * plane bytes = plane bf16 elements
+    }
+    if (nu) {
+        float* tab = reinterpret_cast<float*>(out + 3u * plane);
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < P; j += gridDim.x * blockDim.x) {
+            const float n = j < cols ? nu[j] : 1.0f;
+            tab[0 * P + j] = j < cols ? n + 1.0f : 0.0f;
+            tab[1 * P + j] = n * n;
+            tab[2 * P + j] = j < cols ? b[j] : 0.0f;
+            tab[3 * P + j] = j < cols ? (n + 1.0f) * 0.5f : 0.0f;
+            tab[4 * P + j] = 1.0f / (n * n);
+        }
     }
 }
 
+// 17 warps: the fifth warp of one SM sub-partition caps the allocation at 16384 / (5 * 32) = 102 -> 96 registers
+template <bool POT>
 __global__ void __launch_bounds__(kTcThreads, 1)
-dense_tf32_kernel(const __grid_constant__ LaunchParams p, const float* __restrict__ Btiled) {
+dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
-    __shared__ __align__(8) uint64_t bar_tma, bar_mma;
+    __shared__ __align__(8) uint64_t bar_tma, bar_done, bar_chunk[kTcCPT];
     __shared__ uint32_t s_tmem;
-    __shared__ unsigned long long s_tile;
     __shared__ int s_coin;
-    __shared__ float s_red[4][kTcSplit][kTcTile];     // partial e_start, e_end, ev_start, ev_end per (part, particle)
-    __shared__ unsigned int s_code[kTcTile];          // decision of each particle, broadcast to its 4 threads
+    __shared__ int s_wsum[4];
+    __shared__ float s_red[2][kTcSplit][kTcRows];     // partial H at the start / the end of a trajectory per (slice, row)
+    __shared__ int s_flf_row[kTcRows];                // particle of the chunk -> row of its FLF job, -1 = none
+    __shared__ int s_row_part[kTcRows];               // FLF row -> particle of the chunk
+    __shared__ unsigned int s_code[kTcRows];          // decision of each particle, broadcast to its 4 threads
 
     const int d = p.d;
-    const int ksteps = (d + 7) >> 3;               // MMA K = 8
-    const int N = ((d + 15) >> 4) << 4;            // MMA N: a multiple of 16 for M = 128
-    const int kcores = ksteps * 2;
-    const int ngroups = N >> 3;
-    const uint32_t a_bytes = (uint32_t)kcores * kTcCoreColBytes;
-    const uint32_t b_bytes = (uint32_t)ngroups * kcores * 128u;
-    uint8_t* Ahi = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);
-    uint8_t* Alo = Ahi + a_bytes;
-    uint8_t* Bhi = Alo + a_bytes;
-    uint8_t* Blo = Bhi + b_bytes;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int m = tid & (kTcTile - 1);             // particle of the tile
-    const int q = tid / kTcTile;                   // which slice of the dims
-    const int per = (kcores + kTcSplit - 1) / kTcSplit;
-    const int kc0 = q * per;                       // my core columns [kc0, kc1)
-    const int kc1 = min(kcores, kc0 + per);
-    const bool lead = q == 0;                      // the thread that decides for the particle
+    const int P = ((d + 15) >> 4) << 4;            // padded dims (= experts): N of the MMAs and K in steps of 16
+    const int ncores = P >> 3;
+    const int ksteps = P >> 4;
+    const int nchunks = (ksteps + 1) >> 1;
+    const uint32_t a_plane = (uint32_t)ncores * kTcCoreColBytes;
+    const uint32_t b_plane = (uint32_t)ncores * ncores * 128u;
+    const uint32_t ws_bytes = 3u * b_plane + (POT ? (uint32_t)(kTcTabs * P * 4) : 0u);
+    uint8_t* A0 = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);
+    uint8_t* B0 = A0 + 3u * a_plane;
+    const float* tab = reinterpret_cast<const float*>(B0 + 3u * b_plane);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool epi = tid < kTcEpiThreads;
+    const int m = tid & (kTcRows - 1);             // job row of the tile
+    const int q = (tid >> 7) & 3;                  // which core columns: q, 4+q, 8+q, 12+q
 
-    // ---- one-time setup: barriers, TMEM, the matrix via TMA
+    // ---- one-time setup: barriers, TMEM, the matrix planes via TMA
     if (tid == 0) {
         mbar_init(&bar_tma, 1);
-        mbar_init(&bar_mma, 1);
+        mbar_init(&bar_done, 1);
+#pragma unroll
+        for (int c = 0; c < kTcCPT; ++c) mbar_init(&bar_chunk[c], kTcEpiThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(&s_tmem, kTcTmemCols);
@@ -179,254 +218,331 @@ dense_tf32_kernel(const __grid_constant__ LaunchParams p, const float* __restric
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
     if (tid == 0) {
-        mbar_expect_tx(&bar_tma, 2u * b_bytes);
-        tma_bulk_g2s(Bhi, Btiled, 2u * b_bytes, &bar_tma);
+        mbar_expect_tx(&bar_tma, ws_bytes);
+        tma_bulk_g2s(B0, p.ws, ws_bytes, &bar_tma);
     }
     mbar_wait(&bar_tma, 0);
 
-    // instruction descriptor (cute/arch/mma_sm100_desc.hpp: InstrDescriptor): D = f32, A = B = tf32,
-    // both K-major, N, M = 128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) |
-                           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t a_hi_addr = smem_u32(Ahi), a_lo_addr = smem_u32(Alo);
-    const uint32_t b_hi_addr = smem_u32(Bhi), b_lo_addr = smem_u32(Blo);
-    const uint32_t b_sbo = (uint32_t)kcores * 128u;
-    uint32_t mma_phase = 0;
+    // instruction descriptor (cute/arch/mma_sm100_desc.hpp: InstrDescriptor): D = f32, A = B = bf16, A K-major,
+    // N = P, M = 128; bit 16 selects the MN-major view of B
+    const uint32_t idesc_k = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc_mn = idesc_k | (1u << 16);
+    const uint32_t a_addr = smem_u32(A0), b_addr = smem_u32(B0);
 
     const float eps = (float)p.eps, nhe = (float)(-p.eps / 2.0);
     const int L = p.L, sampler = p.sampler;
+    const bool mj = sampler == MJHMC_SAMPLER_MARKOV_JUMP;
+    const int nprod = POT ? 2 * L + 2 : L + 1;     // products of one tile trajectory
     unsigned int n_l = 0, n_f = 0, n_fl = 0, n_r = 0, n_E = 0, n_exec = 0;
-    unsigned long long* work_head = p.counters + (size_t)MJHMC_COUNTER_STRIPES * MJHMC_N_COUNTERS + 1;
-    // my TMEM window: lane quarter of my warp, columns of my dims (a x32 load may run past them: unused)
-    const uint32_t my_tmem = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kc0 * 4);
+    uint32_t pc = 0;                               // running product counter: barrier parities, accumulator choice
+    // my TMEM window: lane quarter of my warp (warp % 4), accumulator column of core column kc = 8 kc
+    const uint32_t my_lane = (uint32_t)((warp & 3) * 32) << 16;
 
-    float v[kTcDimsPerThread];
+    // contiguous particle range of this CTA
+    const long long r0 = p.n * (long long)blockIdx.x / gridDim.x, r1 = p.n * (long long)(blockIdx.x + 1) / gridDim.x;
 
-    // D = Xtile . S^T for the positions currently in the A tiles (all threads call this)
-    auto tile_gradient = [&]() {
-        fence_async_smem();                        // our generic-proxy stores to A -> visible to the tensor core
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            for (int kg = 0; kg < ksteps; ++kg) {
-                const uint64_t ah = make_desc(a_hi_addr + kg * 2 * kTcCoreColBytes, kTcCoreColBytes, 128, 0);
-                const uint64_t al = make_desc(a_lo_addr + kg * 2 * kTcCoreColBytes, kTcCoreColBytes, 128, 0);
-                const uint64_t bh = make_desc(b_hi_addr + kg * 256, 128, b_sbo, 0);
-                const uint64_t bl = make_desc(b_lo_addr + kg * 256, 128, b_sbo, 0);
-                umma_tf32(tmem_base, ah, bh, idesc, kg > 0 ? 1u : 0u);
-                umma_tf32(tmem_base, al, bh, idesc, 1u);
-                umma_tf32(tmem_base, ah, bl, idesc, 1u);
-            }
-            umma_commit(&bar_mma);
-        }
-        mbar_wait(&bar_mma, mma_phase);
-        mma_phase ^= 1u;
-        tc_fence_after();
-    };
+    float x[kTcCPT][8], v[kTcCPT][8];
 
-    for (;;) {
-        if (tid == 0) s_tile = atomicAdd(work_head, 1ull);
-        __syncthreads();
-        const unsigned long long tile = s_tile;
-        __syncthreads();
-        if ((long long)(tile * kTcTile) >= p.n) break;
-        const long long i = (long long)tile * kTcTile + m;
-        const bool live = i < p.n;
+    for (int it = 0; it < p.n_iter; ++it) {
+        const unsigned long long attempt = p.attempt0 + (unsigned long long)it;
+        const float* Xc = (const float*)(it == 0 ? p.Xin : p.Xout);
+        const float* Vc = (const float*)(it == 0 ? p.Vin : p.Vout);
+        const uint8_t* cac = it == 0 ? p.ca_in : p.ca_out;
+        const float* Hcc = (const float*)(it == 0 ? p.Hc_in : p.Hc_out);
+        float* Xo = (float*)p.Xout;
+        float* Vo = (float*)p.Vout;
+        if (sampler == MJHMC_SAMPLER_DISCRETE && tid == 0) s_coin = draw_coin(p, attempt) < p.p_r;
 
-        unsigned int cflags = 0;
-        float Hc = 0.0f;
-        double dwell = 0.0;
-        bool failed = false;
-        if (lead && live && sampler == MJHMC_SAMPLER_MARKOV_JUMP) { cflags = p.ca_in[i]; Hc = ((const float*)p.Hc_in)[i]; }
-
-        for (int it = 0; it < p.n_iter; ++it) {
-            const unsigned long long attempt = p.attempt0 + (unsigned long long)it;
-            const float* Xc = (const float*)(it == 0 ? p.Xin : p.Xout);
-            const float* Vc = (const float*)(it == 0 ? p.Vin : p.Vout);
-            float* Xo = (float*)p.Xout;
-            float* Vo = (float*)p.Vout;
-            const bool active = lead && live && !failed;
-            if (sampler == MJHMC_SAMPLER_DISCRETE) {
-                if (tid == 0) s_coin = draw_coin(p, attempt) < p.p_r;
-            }
-
-            float Hflf = Hc, H = 0.0f, Hl = 0.0f;
-            bool need = false;
-            if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
-                need = active && !(cflags & 2u);
-                if (active && !(cflags & 1u)) n_E += 1;
-            }
-            const int first_pass = __syncthreads_or(need ? 1 : 0) ? 0 : 1;
-            const bool coin_fired = s_coin != 0;                       // read behind the barrier above
-
-            for (int pass = first_pass; pass < 2; ++pass) {
-                // ---- load my slice of (x, +-v); x goes to the A tiles split into hi / lo
-                const float sign = pass == 0 ? -1.0f : 1.0f;
-                float ev = 0.0f;
+        for (long long cur = r0; cur < r1;) {
+            // ---- plan the tile: particles cur .. cur+np-1 with np + #FLF jobs <= 128
+            unsigned int cflags = 0;
+            int need = 0, valid = 0, incl = 0;
+            if (tid < kTcRows) {
+                const long long i = cur + tid;
+                valid = i < r1;
+                if (valid && mj) { cflags = cac[i]; need = !(cflags & 2u); }
+                incl = valid ? 1 + need : 0;
 #pragma unroll
-                for (int j = 0; j < kTcDimsPerThread; ++j) v[j] = 0.0f;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (lane == 31) s_wsum[warp] = incl;
+            }
+            __syncthreads();
+            if (tid < kTcRows) {
+                for (int w = 0; w < warp; ++w) incl += s_wsum[w];
+                s_flf_row[tid] = -1;
+            }
+            const int np = __syncthreads_count(tid < kTcRows && valid && incl <= kTcRows);
+            const bool mine = tid < np;                                     // lead thread of an L job
+            if (mine && need) {
+                const int row = np + (incl - (tid + 1) - 1);                // FLF rows follow the L rows, in particle order
+                s_flf_row[tid] = row;
+                s_row_part[row] = tid;
+            }
+            __syncthreads();
+            const int nflf = __syncthreads_count(mine && need);
+            const int nrows = np + nflf;
+
+            // ---- my job: row m -> (particle, sign)
+            const bool is_l = epi && m < np, is_flf = epi && m >= np && m < nrows;
+            const int part = is_l ? m : (is_flf ? s_row_part[m] : 0);
+            const long long i = cur + part;
+            const float sign = is_flf ? -1.0f : 1.0f;
+            const bool live = is_l || is_flf;
+
+            if (epi) {
+                // ---- load my slice of (x, +-v)
+                float ev0 = 0.0f;
 #pragma unroll
-                for (int h = 0; h < kTcCoresPerThread; ++h) {
-                    const int kc = kc0 + h;
-                    if (kc < kc1) {
-                        float xs[4];
+                for (int c = 0; c < kTcCPT; ++c) {
+                    const int kc = 4 * c + q;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int k = kc * 4 + j;
-                            xs[j] = 0.0f;
-                            v[h * 4 + j] = 0.0f;
-                            if (live && k < d) { xs[j] = Xc[(long long)k * p.ld + i]; v[h * 4 + j] = sign * Vc[(long long)k * p.ld + i]; }
-                            ev += v[h * 4 + j] * v[h * 4 + j];
-                        }
-                        const float4 hi = make_float4(tf32_hi(xs[0]), tf32_hi(xs[1]), tf32_hi(xs[2]), tf32_hi(xs[3]));
-                        const uint32_t off = a_row_offset(m, kc);
-                        *reinterpret_cast<float4*>(Ahi + off) = hi;
-                        *reinterpret_cast<float4*>(Alo + off) = make_float4(xs[0] - hi.x, xs[1] - hi.y, xs[2] - hi.z, xs[3] - hi.w);
+                    for (int j = 0; j < 8; ++j) {
+                        const int k = kc * 8 + j;
+                        x[c][j] = 0.0f; v[c][j] = 0.0f;
+                        if (live && k < d) { x[c][j] = Xc[(long long)k * p.ld + i]; v[c][j] = sign * Vc[(long long)k * p.ld + i]; }
+                        ev0 += v[c][j] * v[c][j];
                     }
                 }
                 float e_start = 0.0f, e_end = 0.0f;
 
+                // ---- first A operand: the positions
+#pragma unroll
+                for (int c = 0; c < kTcCPT; ++c) {
+                    if (c < nchunks) {
+                        const int kc = 4 * c + q;
+                        if (kc < ncores) split3_store(x[c], A0, a_plane, a_row_offset(m, kc));
+                        fence_async_smem();
+                        tc_fence_before();
+                        mbar_arrive(&bar_chunk[c]);
+                    }
+                }
+
                 for (int st = 0; st <= L; ++st) {
-                    tile_gradient();
-                    // ---- sweep over my slice of my particle's gradient (one TMEM round trip)
-                    float g[32];
-                    tmem_ld32(my_tmem, g);
+                    if (POT) {
+                        // ---- phase 1: Y = X W + b  ->  G (and the energy at the two ends of the trajectory)
+                        mbar_wait(&bar_done, pc & 1u);
+                        tc_fence_after();
+                        ++pc;
 #pragma unroll
-                    for (int h = 0; h < kTcCoresPerThread; ++h) {
-                        const int kc = kc0 + h;
-                        if (kc < kc1) {
-                            const uint32_t off = a_row_offset(m, kc);
-                            float4* ph = reinterpret_cast<float4*>(Ahi + off);
-                            float4* pl = reinterpret_cast<float4*>(Alo + off);
-                            const float4 xh = *ph, xl = *pl;
-                            float xs[4] = {xh.x + xl.x, xh.y + xl.y, xh.z + xl.z, xh.w + xl.w};
+                        for (int c = 0; c < kTcCPT; ++c) {
+                            if (c < nchunks) {
+                                const int kc = 4 * c + q;
+                                if (kc < ncores) {
+                                    float y[8];
+                                    tmem_ld8(tmem_base + my_lane + (uint32_t)(kc * 8), y);
+                                    const float4* t4 = reinterpret_cast<const float4*>(tab);
+                                    float a1[8], n2[8], bb[8];
+                                    *reinterpret_cast<float4*>(a1) = t4[(0 * P + kc * 8) >> 2]; *reinterpret_cast<float4*>(a1 + 4) = t4[((0 * P + kc * 8) >> 2) + 1];
+                                    *reinterpret_cast<float4*>(n2) = t4[(1 * P + kc * 8) >> 2]; *reinterpret_cast<float4*>(n2 + 4) = t4[((1 * P + kc * 8) >> 2) + 1];
+                                    *reinterpret_cast<float4*>(bb) = t4[(2 * P + kc * 8) >> 2]; *reinterpret_cast<float4*>(bb + 4) = t4[((2 * P + kc * 8) >> 2) + 1];
+                                    if (st == 0 || st == L) {
+                                        float e = 0.0f;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float gk = g[h * 4 + j];
-                                float vv = v[h * 4 + j];
-                                e_start += st == 0 ? xs[j] * gk : 0.0f;
-                                e_end += st == L ? xs[j] * gk : 0.0f;
-                                vv += st > 0 ? nhe * gk : 0.0f;        // second half kick of step st
-                                vv += st < L ? nhe * gk : 0.0f;        // first half kick of step st+1
-                                xs[j] += st < L ? eps * vv : 0.0f;     // drift of step st+1
-                                v[h * 4 + j] = vv;
+                                        for (int j = 0; j < 8; ++j) {
+                                            const float yy = y[j] + bb[j];
+                                            e += tab[3 * P + kc * 8 + j] * log1pf(yy * yy * tab[4 * P + kc * 8 + j]);   // :431
+                                        }
+                                        if (st == 0) e_start += e;
+                                        if (st == L) e_end += e;
+                                    }
+                                    float g[8];
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float yy = y[j] + bb[j];
+                                        g[j] = __fdividef(a1[j] * yy, n2[j] + yy * yy);
+                                    }
+                                    split3_store(g, A0, a_plane, a_row_offset(m, kc));
+                                }
+                                fence_async_smem();
+                                tc_fence_before();
+                                mbar_arrive(&bar_chunk[c]);
+                            }
+                        }
+                    }
+                    // ---- gradient sweep: kick, drift, next positions
+                    mbar_wait(&bar_done, pc & 1u);
+                    tc_fence_after();
+                    const uint32_t dcol = tmem_base + my_lane + (POT ? 128u : ((pc & 1u) ? 128u : 0u));
+                    ++pc;
+#pragma unroll
+                    for (int c = 0; c < kTcCPT; ++c) {
+                        if (c < nchunks) {
+                            const int kc = 4 * c + q;
+                            if (kc < ncores) {
+                                float g[8];
+                                tmem_ld8(dcol + (uint32_t)(kc * 8), g);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float gk = g[j];
+                                    float vv = v[c][j];
+                                    if (!POT) {
+                                        e_start += st == 0 ? x[c][j] * gk : 0.0f;      // E = x.(S x)/2
+                                        e_end += st == L ? x[c][j] * gk : 0.0f;
+                                    }
+                                    vv += st > 0 ? nhe * gk : 0.0f;        // second half kick of step st
+                                    vv += st < L ? nhe * gk : 0.0f;        // first half kick of step st+1
+                                    x[c][j] += st < L ? eps * vv : 0.0f;   // drift of step st+1
+                                    v[c][j] = vv;
+                                }
+                                if (st < L) split3_store(x[c], A0, a_plane, a_row_offset(m, kc));
                             }
                             if (st < L) {
-                                const float4 hi = make_float4(tf32_hi(xs[0]), tf32_hi(xs[1]), tf32_hi(xs[2]), tf32_hi(xs[3]));
-                                *ph = hi;
-                                *pl = make_float4(xs[0] - hi.x, xs[1] - hi.y, xs[2] - hi.z, xs[3] - hi.w);
+                                fence_async_smem();
+                                tc_fence_before();
+                                mbar_arrive(&bar_chunk[c]);
                             }
                         }
                     }
                 }
+                if (!POT) { e_start *= 0.5f; e_end *= 0.5f; }
                 if (L == 0) e_end = e_start;
-                float ev_end = 0.0f;
+                float ev1 = 0.0f;
 #pragma unroll
-                for (int j = 0; j < kTcDimsPerThread; ++j) ev_end += v[j] * v[j];   // slots beyond my dims hold 0
-                // ---- per-particle totals: the four slices meet in shared memory
-                s_red[0][q][m] = e_start; s_red[1][q][m] = e_end; s_red[2][q][m] = ev; s_red[3][q][m] = ev_end;
-                __syncthreads();
-                if (lead) {
-                    float t[4];
+                for (int c = 0; c < kTcCPT; ++c)
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        t[r] = 0.0f;
+                    for (int j = 0; j < 8; ++j) ev1 += v[c][j] * v[c][j];       // slots beyond my dims hold 0
+                s_red[0][q][m] = e_start + 0.5f * ev0;                          // EX + EV, hmc_state.py:80-84
+                s_red[1][q][m] = e_end + 0.5f * ev1;
+            } else {
+                // ---- the MMA warp: chunk c of a product is issued as soon as its 512 writers have arrived
+                for (int prod = 0; prod < nprod; ++prod) {
+                    const bool y_prod = POT && !(prod & 1);                      // Y = X W: B read MN-major (K = dims)
+                    const uint32_t dacc = tmem_base + (POT ? (y_prod ? 0u : 128u) : ((pc & 1u) ? 128u : 0u));
+                    for (int c = 0; c < nchunks; ++c) {
+                        mbar_wait(&bar_chunk[c], pc & 1u);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const int kg1 = min(ksteps, 2 * c + 2);
+                            for (int kg = 2 * c; kg < kg1; ++kg) {
+                                uint64_t ad[3], bd[3];
 #pragma unroll
-                        for (int qq = 0; qq < kTcSplit; ++qq) t[r] += s_red[r][qq][m];
+                                for (int pl = 0; pl < 3; ++pl) {
+                                    ad[pl] = make_desc(a_addr + pl * a_plane + kg * 2 * kTcCoreColBytes, kTcCoreColBytes, 128);
+                                    bd[pl] = y_prod ? make_desc(b_addr + pl * b_plane + kg * 2 * ncores * 128, ncores * 128, 128)
+                                                    : make_desc(b_addr + pl * b_plane + kg * 256, 128, ncores * 128);
+                                }
+                                const uint32_t idesc = y_prod ? idesc_mn : idesc_k;
+                                umma_bf16(dacc, ad[0], bd[0], idesc, kg > 0 ? 1u : 0u);
+                                umma_bf16(dacc, ad[0], bd[1], idesc, 1u);
+                                umma_bf16(dacc, ad[1], bd[0], idesc, 1u);
+                                umma_bf16(dacc, ad[1], bd[1], idesc, 1u);
+                                umma_bf16(dacc, ad[0], bd[2], idesc, 1u);
+                                umma_bf16(dacc, ad[2], bd[0], idesc, 1u);
+                            }
+                            if (c == nchunks - 1) umma_commit(&bar_done);
+                        }
+                        __syncwarp();
                     }
-                    const float h_start = 0.5f * t[0] + 0.5f * t[2];   // EX + EV, hmc_state.py:80-84
-                    const float h_end = 0.5f * t[1] + 0.5f * t[3];
-                    if (pass == 0) { if (need) { Hflf = h_end; n_exec += 1; } }
-                    else { H = h_start; Hl = h_end; }
+                    ++pc;
                 }
             }
-            if (active) { n_E += 1; n_exec += 1; }
+            __syncthreads();
 
-            // ---- decision by the lead thread of each particle (same device code as the register-resident kernel)
-            unsigned int take = 0, flip = 0, refresh = 0, choice = 0;
-            if (active) {
-                if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
-                    const Decision dc = decide_mj(p, i, attempt, (double)(H - Hl), (double)(H - Hflf));
-                    if (dc.fail) { report_failure(p, it); failed = true; }
+            // ---- decision by the lead thread of each L job (same device code as the register-resident kernel)
+            unsigned int take = 0, flip = 0, refresh = 0, choice = 0, ok = 0;
+            double dwell = 0.0;
+            if (mine) {
+                float H = 0.0f, Hl = 0.0f, Hflf = 0.0f;
+#pragma unroll
+                for (int qq = 0; qq < kTcSplit; ++qq) { H += s_red[0][qq][tid]; Hl += s_red[1][qq][tid]; }
+                n_E += 1; n_exec += 1;
+                float Hc = 0.0f;
+                if (mj) {
+                    if (!(cflags & 1u)) n_E += 1;                  // the reference evaluates the FLF state here
+                    if (need) {
+                        const int fr = s_flf_row[tid];
+#pragma unroll
+                        for (int qq = 0; qq < kTcSplit; ++qq) Hflf += s_red[1][qq][fr];
+                        n_exec += 1;
+                    } else {
+                        Hflf = Hcc[cur + tid];
+                    }
+                    const Decision dc = decide_mj(p, cur + tid, attempt, (double)(H - Hl), (double)(H - Hflf));
+                    if (dc.fail) report_failure(p, it);
                     else {
-                        choice = dc.choice; dwell = dc.dwell;
+                        ok = 1; choice = dc.choice; dwell = dc.dwell;
                         if (choice == 0) { take = 1; Hc = H; cflags = 3u; n_l += 1; }
                         else if (choice == 1) { flip = 1; Hc = Hl; cflags = 2u; n_f += 1; }
-                        else { refresh = 1; cflags = 0u; n_r += 1; }
+                        else { refresh = 1; Hc = Hflf; cflags = 0u; n_r += 1; }
                     }
+                    if (!ok) Hc = need ? 0.0f : Hflf;
+                    p.ca_out[cur + tid] = (uint8_t)(ok ? cflags : (need ? (cflags & ~2u) : cflags));
+                    ((float*)p.Hc_out)[cur + tid] = Hc;
                 } else if (sampler == MJHMC_SAMPLER_CONTINUOUS_TIME) {
-                    const Decision dc = decide_ct(p, i, attempt, (double)(H - Hl));
-                    if (dc.fail) { report_failure(p, it); failed = true; }
+                    const Decision dc = decide_ct(p, cur + tid, attempt, (double)(H - Hl));
+                    if (dc.fail) report_failure(p, it);
                     else {
-                        choice = dc.choice; dwell = dc.dwell;
+                        ok = 1; choice = dc.choice; dwell = dc.dwell;
                         if (choice == 1) { take = 2; n_fl += 1; }
                         else if (choice == 0) { flip = 1; n_f += 1; }
                         else { refresh = 1; n_r += 1; }
                     }
                 } else {
-                    const Decision dc = decide_discrete(p, i, attempt, (double)(H - Hl), coin_fired);
-                    choice = dc.choice;
+                    const Decision dc = decide_discrete(p, cur + tid, attempt, (double)(H - Hl), s_coin != 0);
+                    ok = 1; choice = dc.choice;
                     const bool acc = choice & 1u, fl = choice & 2u;
                     if (acc) take = 2;
                     flip = fl; refresh = (choice & 4u) ? 1u : 0u;
                     n_l += (acc && fl); n_f += (fl && !acc); n_fl += (acc && !fl); n_r += refresh;
                 }
+                s_code[tid] = take | (flip << 2) | (refresh << 3) | (ok << 4);
+                if (ok) {
+                    if (p.dwell) p.dwell[(long long)it * p.n + cur + tid] = dwell;
+                    if (p.choice) p.choice[(long long)it * p.n + cur + tid] = (uint8_t)choice;
+                    if (p.dwell_last && sampler != MJHMC_SAMPLER_DISCRETE) p.dwell_last[cur + tid] = dwell;
+                }
             }
-            if (lead) s_code[m] = take | (flip << 2) | (refresh << 3) | ((active && !failed) ? 16u : 0u);
             __syncthreads();
-            const unsigned int code = s_code[m];
-            const unsigned int tk = code & 3u;
-            const bool fp = code & 4u, rf = code & 8u, ok = code & 16u;
 
             // ---- apply: my slice of my particle's new state goes to the output arrays
-            if (live) {
+            if (is_l) {
+                const unsigned int code = s_code[m];
+                const unsigned int tk = code & 3u;
+                const bool fp = code & 4u, rf = code & 8u, okk = code & 16u;
 #pragma unroll
-                for (int h = 0; h < kTcCoresPerThread; ++h) {
-                    const int kc = kc0 + h;
-                    if (kc < kc1) {
-                        const uint32_t off = a_row_offset(m, kc);
-                        const float4 xh = *reinterpret_cast<const float4*>(Ahi + off), xl = *reinterpret_cast<const float4*>(Alo + off);
-                        const float xt[4] = {xh.x + xl.x, xh.y + xl.y, xh.z + xl.z, xh.w + xl.w};
+                for (int c = 0; c < kTcCPT; ++c) {
+                    const int kc = 4 * c + q;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int k = kc * 4 + j;
-                            if (k < d) {
-                                const long long o = (long long)k * p.ld + i;
-                                float xn, vn;
-                                if (ok && tk) { xn = xt[j]; vn = tk == 1 ? v[h * 4 + j] : -v[h * 4 + j]; }
-                                else { xn = Xc[o]; vn = Vc[o]; }
-                                if (ok && fp) vn = -vn;
-                                if (ok && rf) {
-                                    double z0, z1;
-                                    normal_pair(p, i, attempt, k >> 1, d, z0, z1);
-                                    vn = vn * (float)p.r_keep + (float)((k & 1) ? z1 : z0) * (float)p.r_mix;   // hmc_state.py:126
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int k0 = kc * 8 + 2 * jj;                     // dims k0, k0+1 share one Box-Muller pair
+                        if (k0 < d) {
+                            double z[2] = {0.0, 0.0};
+                            if (okk && rf) normal_pair(p, i, attempt, k0 >> 1, d, z[0], z[1]);
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int k = k0 + e, j = 2 * jj + e;
+                                if (k < d) {
+                                    const long long o = (long long)k * p.ld + i;
+                                    float xn, vn;
+                                    if (okk && tk) { xn = x[c][j]; vn = tk == 1 ? v[c][j] : -v[c][j]; }
+                                    else { xn = Xc[o]; vn = Vc[o]; }
+                                    if (okk && fp) vn = -vn;
+                                    if (okk && rf) vn = vn * (float)p.r_keep + (float)z[e] * (float)p.r_mix;   // hmc_state.py:126
+                                    Xo[o] = xn;
+                                    Vo[o] = vn;
+                                    if (okk && p.samples) ((float*)p.samples)[(long long)k * p.s_stride_k + (long long)it * p.s_stride_it + i] = xn;
                                 }
-                                Xo[o] = xn;
-                                Vo[o] = vn;
-                                if (ok && p.samples) ((float*)p.samples)[(long long)k * p.s_stride_k + (long long)it * p.s_stride_it + i] = xn;
                             }
                         }
                     }
                 }
-                if (lead && ok) {
-                    if (p.dwell) p.dwell[(long long)it * p.n + i] = dwell;
-                    if (p.choice) p.choice[(long long)it * p.n + i] = (uint8_t)choice;
-                }
             }
-            __syncthreads();                       // s_code / s_red / the A tiles are reused by the next iteration
+            __syncthreads();                       // the tables, s_red and the A planes are reused by the next tile
+            cur += np;
         }
-        if (live) {
-            if (lead) {
-                if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) { p.ca_out[i] = (uint8_t)cflags; ((float*)p.Hc_out)[i] = Hc; }
-                if (p.dwell_last && sampler != MJHMC_SAMPLER_DISCRETE) p.dwell_last[i] = dwell;
+    }
+    if (p.n_iter == 0) {
+        for (long long i = r0 + tid; i < r1; i += kTcThreads)
+            for (int k = 0; k < d; ++k) {
+                ((float*)p.Xout)[(long long)k * p.ld + i] = ((const float*)p.Xin)[(long long)k * p.ld + i];
+                ((float*)p.Vout)[(long long)k * p.ld + i] = ((const float*)p.Vin)[(long long)k * p.ld + i];
             }
-            if (p.n_iter == 0) {
-                for (int k = kc0 * 4; k < min(d, kc1 * 4); ++k) {
-                    ((float*)p.Xout)[(long long)k * p.ld + i] = ((const float*)p.Xin)[(long long)k * p.ld + i];
-                    ((float*)p.Vout)[(long long)k * p.ld + i] = ((const float*)p.Vin)[(long long)k * p.ld + i];
-                }
-            }
+        if (mj) for (long long i = r0 + tid; i < r1; i += kTcThreads) {
+            p.ca_out[i] = p.ca_in[i];
+            ((float*)p.Hc_out)[i] = ((const float*)p.Hc_in)[i];
         }
     }
 
@@ -438,47 +554,53 @@ dense_tf32_kernel(const __grid_constant__ LaunchParams p, const float* __restric
     flush_counters(p.counters, loc, (unsigned long long)L);
 }
 
-bool dense_tf32_supported(int kind, int ndims) {
-    return kind == MJHMC_DIST_DENSE_GAUSSIAN && ndims >= 1 && ndims <= kTcMaxDim;
+bool dense_tc_supported(int kind, int ndims, int nbasis) {
+    if (ndims < 1 || ndims > kTcMaxP) return false;
+    if (kind == MJHMC_DIST_DENSE_GAUSSIAN) return true;
+    return kind == MJHMC_DIST_PRODUCT_OF_T && nbasis == ndims;
 }
 
-static void tf32_shape(int d, int& ksteps, int& N, int& kcores, int& ngroups) {
-    ksteps = (d + 7) >> 3; N = ((d + 15) >> 4) << 4; kcores = ksteps * 2; ngroups = N >> 3;
+static void tc_shape(int d, int& P, int& ncores) { P = ((d + 15) >> 4) << 4; ncores = P >> 3; }
+
+long long dense_tc_workspace_bytes(int kind, int ndims) {
+    int P, nc;
+    tc_shape(ndims, P, nc);
+    return 3ll * nc * nc * 128 + (kind == MJHMC_DIST_PRODUCT_OF_T ? (long long)kTcTabs * P * 4 : 0);
 }
 
-long long dense_tf32_workspace_bytes(int ndims) {
-    int ksteps, N, kcores, ngroups;
-    tf32_shape(ndims, ksteps, N, kcores, ngroups);
-    return 2ll * ngroups * kcores * 128;
-}
-
-// Fills the pre-tiled hi / lo copy of S (once per distribution; the sampler launches only read it).
-cudaError_t dense_tf32_prepare(const float* S, int ndims, float* workspace, cudaStream_t stream) {
-    int ksteps, N, kcores, ngroups;
-    tf32_shape(ndims, ksteps, N, kcores, ngroups);
-    tf32_prep_kernel<<<32, 256, 0, stream>>>(S, ndims, ngroups, kcores, workspace);
+// Fills the pre-tiled bf16 planes (once per distribution; the sampler launches only read them).
+cudaError_t dense_tc_prepare(int kind, const float* Mx, const float* nu, const float* b, int ndims, void* workspace,
+                             cudaStream_t stream) {
+    int P, nc;
+    tc_shape(ndims, P, nc);
+    const bool pot = kind == MJHMC_DIST_PRODUCT_OF_T;
+    tc_prep_kernel<<<32, 256, 0, stream>>>(Mx, ndims, ndims, P, pot ? nu : nullptr, pot ? b : nullptr, (uint8_t*)workspace);
     return cudaGetLastError();
 }
 
-cudaError_t launch_dense_tf32(const LaunchParams& p, cudaStream_t stream) {
-    int ksteps, N, kcores, ngroups;
-    tf32_shape(p.d, ksteps, N, kcores, ngroups);
-    if (!p.a1) return cudaErrorInvalidValue;                   // the pre-tiled matrix (mjhmc_dense_tf32_prepare)
-    const size_t a_bytes = (size_t)kcores * kTcCoreColBytes;
-    const size_t b_bytes = (size_t)ngroups * kcores * 128;
-    const size_t smem = 2 * a_bytes + 2 * b_bytes + 1024;
+template <bool POT>
+static cudaError_t launch_tc_T(const LaunchParams& p, cudaStream_t stream) {
+    int P, nc;
+    tc_shape(p.d, P, nc);
+    const size_t smem = 3 * (size_t)nc * kTcCoreColBytes + 3 * (size_t)nc * nc * 128 + (POT ? kTcTabs * P * 4 : 0) + 1024;
     static int sms = 0;
     if (!sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    cudaError_t e = cudaFuncSetAttribute(dense_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel<POT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    long long tiles = (p.n + kTcTile - 1) / kTcTile;
-    if (tiles > sms) tiles = sms;
-    dense_tf32_kernel<<<(unsigned)tiles, kTcThreads, smem, stream>>>(p, (const float*)p.a1);
+    long long blocks = (p.n + 95) / 96;            // ~one tile of jobs per CTA at the least
+    if (blocks > sms) blocks = sms;
+    if (blocks < 1) blocks = 1;
+    dense_tc_kernel<POT><<<(unsigned)blocks, kTcThreads, smem, stream>>>(p);
     return cudaGetLastError();
+}
+
+cudaError_t launch_dense_tc(int kind, const LaunchParams& p, cudaStream_t stream) {
+    if (!p.ws) return cudaErrorInvalidValue;                   // the pre-tiled matrix (mjhmc_dense_tc_prepare)
+    return kind == MJHMC_DIST_PRODUCT_OF_T ? launch_tc_T<true>(p, stream) : launch_tc_T<false>(p, stream);
 }
 
 }  // namespace mjhmc

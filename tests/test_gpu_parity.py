@@ -304,17 +304,19 @@ def test_dense_kernel_matches_oracle(kind, dist_name, d):
     assert s._engine.launches == 1
 
 
-@pytest.mark.parametrize("kind", ["ControlHMC", "ContinuousTimeHMC", "MarkovJumpHMC"])
-@pytest.mark.parametrize("d,N", [(12, 40), (40, 300), (100, 517)])
-def test_dense_gaussian_float32_tcgen05(kind, d, N):
-    """fp32 states: the tcgen05 / TMEM / TMA kernel with 3xTF32 operands against the fp64 oracle (1e-4)."""
+@pytest.mark.parametrize("kind", orc.KINDS)
+@pytest.mark.parametrize("dist_name,d,N", [("Gaussian", 12, 40), ("Gaussian", 40, 300), ("Gaussian", 100, 517),
+                                           ("ProductOfT", 6, 40), ("ProductOfT", 36, 300), ("ProductOfT", 100, 517)])
+def test_dense_float32_tcgen05(kind, dist_name, d, N):
+    """fp32 states: the tcgen05 / TMEM / TMA kernel (bf16x3 operands, csrc/dense_tc.cu) against the fp64 oracle (1e-4),
+    full-covariance Gaussian and ProductOfT, all sampler classes, several iterations in one launch."""
     from mjhmc_b200.samplers import markov_jump_hmc as S
     rs = np.random.RandomState(50 + d)
-    dist, energy, X0 = _dense_case("Gaussian", d, N, rs)
+    dist, energy, X0 = _dense_case(dist_name, d, N, rs)
     V0 = rs.randn(d, N)
     helpers.pin_init(dist, X0)
     hp = dict(epsilon=0.1, beta=0.3, num_leapfrog_steps=3)
-    extra = dict(resample=False) if kind != "ControlHMC" else {}
+    extra = dict(resample=False) if kind in ("ContinuousTimeHMC", "MarkovJumpHMC") else {}
     s = getattr(S, kind)(distribution=dist, V=V0, seed=3, dtype="float32", particle_offset=7, **hp, **extra)
     assert s._engine.fused
     o = orc.OracleSampler(kind, energy, X0, V=V0, draws=orc.PhiloxDraws(3, 7), resample=False, **hp)
@@ -331,19 +333,61 @@ def test_dense_gaussian_float32_tcgen05(kind, d, N):
     assert s._engine.launches == 1
 
 
-def test_dense_float32_product_of_t_uses_unfused_device_path():
-    """ProductOfT with fp32 states has no fused kernel yet: the sampler must still run on the GPU (unfused
-    pieces + device gradient kernels) and agree with the fp64 oracle to fp32 accuracy."""
+@pytest.mark.parametrize("dist_name", ["Gaussian", "ProductOfT"])
+def test_dense_float32_single_iteration_from_oracle_state(dist_name):
+    """fp32 tcgen05 kernel, MarkovJumpHMC, each iteration restarted from the oracle's fp64 state (no error accumulation,
+    FLF cache hits and misses mixed inside a tile): trajectories to 1e-4, operator choices and counters exact up to
+    float32 near-ties."""
     from mjhmc_b200.samplers import markov_jump_hmc as S
-    rs = np.random.RandomState(5)
-    dist, energy, X0 = _dense_case("ProductOfT", 12, 40, rs)
-    V0 = rs.randn(12, 40)
+    d, N = 100, 700
+    rs = np.random.RandomState(9)
+    dist, energy, X0 = _dense_case(dist_name, d, N, rs)
+    V0 = rs.randn(d, N)
     helpers.pin_init(dist, X0)
-    hp = dict(epsilon=0.1, beta=0.3, num_leapfrog_steps=3)
-    s = S.ControlHMC(distribution=dist, V=V0, seed=3, dtype="float32", **hp)
-    assert not s._engine.fused
-    o = orc.OracleSampler("ControlHMC", energy, X0, V=V0, draws=orc.PhiloxDraws(3), **hp)
-    X, Xo = s.sample(2), o.sample(2)
-    same = np.all(np.abs(X - Xo) <= 1e-3 * (1 + np.abs(Xo)), axis=0)
-    assert same.mean() > 0.95
-    assert helpers.rel_err32(X[:, same], Xo[:, same]) < 1e-4
+    hp = dict(epsilon=0.1, beta=0.3, num_leapfrog_steps=4)
+    s = S.MarkovJumpHMC(distribution=dist, V=V0, seed=11, dtype="float32", resample=False, **hp)
+    o = orc.OracleSampler("MarkovJumpHMC", energy, X0, V=V0, draws=orc.PhiloxDraws(11), resample=False, **hp)
+    flips = 0
+    for it in range(6):
+        st = s.state
+        st.X[:], st.V[:] = o.X, o.V
+        st.cache_active[:], st.H_cache[:] = o.cache_active, o.H_cache
+        s.state = st
+        s._attempt = o.attempt
+        o.sampling_iteration()
+        _, _, ch = s._advance(1, want_choice=True)
+        got = s.state
+        same = ch[0].cpu().numpy() == o.last_choice
+        flips += int((~same).sum())
+        assert helpers.rel_err32(got.X[:, same], o.X[:, same]) < 1e-4, it
+        assert helpers.rel_err32(got.V[:, same], o.V[:, same]) < 1e-4, it
+        np.testing.assert_array_equal(got.cache_active[same], o.cache_active[same])
+        s._host_state = None
+    assert flips <= 6, flips
+
+
+@pytest.mark.parametrize("dist_name", ["Gaussian", "ProductOfT"])
+def test_dense_float32_rows_do_not_depend_on_the_tile_packing(dist_name):
+    """The tcgen05 kernel packs L jobs and the FLF jobs of uncached particles into 128-row tiles whose composition
+    depends on the particle range of the CTA: the whole cloud and two unequal shards must give bit-identical samples
+    (rows of an MMA are independent), with identical counters."""
+    from mjhmc_b200.samplers import markov_jump_hmc as S
+    d, N, n = 36, 1000, 6
+    rs = np.random.RandomState(4)
+    dist0, energy, X0 = _dense_case(dist_name, d, N, rs)
+    V0 = rs.randn(d, N)
+    hp = dict(epsilon=0.2, beta=0.3, num_leapfrog_steps=3)
+    outs, cnts = [], []
+    for bounds in ([(0, N)], [(0, 333), (333, N)]):
+        parts, tot = [], np.zeros(6, dtype=np.int64)
+        for lo, hi in bounds:
+            dist, _, _ = _dense_case(dist_name, d, hi - lo, np.random.RandomState(4))
+            helpers.pin_init(dist, X0[:, lo:hi])
+            s = S.MarkovJumpHMC(distribution=dist, V=V0[:, lo:hi], seed=5, dtype="float32", resample=False,
+                                particle_offset=lo, **hp)
+            parts.append(s.sample(n, preserve_order=True))
+            tot += np.array(_counters(s, dist))
+        outs.append(np.concatenate(parts, axis=1))
+        cnts.append(tot)
+    np.testing.assert_array_equal(outs[0], outs[1])
+    np.testing.assert_array_equal(cnts[0], cnts[1])
