@@ -117,6 +117,16 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_bf16_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            j = json.load(f)
+        if "bf16_tflops_sustained" in j:
+            return float(j["bf16_tflops_sustained"]), "measured dense bf16 %.0f TFLOP/s (MEASURED_PEAKS.json, sustained)" % j["bf16_tflops_sustained"]
+    return 2250.0, "nominal dense bf16 2250 TFLOP/s (B200_PROFILING.md fallback)"
+
+
 def algorithmic_bytes_per_launch(w, S=None):
     S = S or (4 if w.get("dtype") == "float32" else 8)
     """DESIGN.md 'Algorithmic traffic': per particle, one launch of `iters` iterations reads X,V,
@@ -415,9 +425,9 @@ class Ctx(object):
 
 
 def measured_tensor_peaks(ctx):
-    """cuBLAS GEMM rates of THIS GPU for the two tensor-core number formats the dense kernels use (fp64 DMMA and
-    tf32): the denominators of the tensor rooflines.  MEASURED_PEAKS.json only holds a bf16 figure, which applies to
-    neither; best of 5 runs of a 6144^3 (fp64) / 8192^3 (tf32) torch.matmul, CUDA events."""
+    """cuBLAS GEMM rates of THIS GPU for fp64 (DMMA, the denominator of the fp64 dense kernels' roofline:
+    MEASURED_PEAKS.json only holds a bf16 figure) and, for reference, tf32; best of 5 runs of a 6144^3 (fp64) /
+    8192^3 (tf32) torch.matmul, CUDA events."""
     torch = ctx.torch
     out = {}
     old = torch.backends.cuda.matmul.allow_tf32
@@ -512,16 +522,18 @@ def roofline_of(ctx, m, peaks):
         tf = m["grads_all"] * fl / (m["ms_max"] * 1e-3) / 1e12 / world
         f32 = w.get("dtype") == "float32"
         if f32:
-            tpeak = peaks.get("tf32_tflops", 1100.0) / 3.0
-            src = ("cuBLAS tf32 GEMM measured in this run (%.0f TFLOP/s) divided by the 3 MMAs of the 3xTF32 split"
-                   % peaks["tf32_tflops"]) if "tf32_tflops" in peaks else "nominal 1.1 PFLOP/s tf32 / 3"
+            # bf16x3 operands: one product = 6 bf16 MMAs (csrc/dense_tc.cu); the denominator is the measured dense bf16
+            # rate of this pool's B200s (MEASURED_PEAKS.json, sustained figure: the kernel runs for milliseconds)
+            bf16 = measured_bf16_peak()
+            tpeak = bf16[0] / 6.0
+            src = "%s / 6 bf16 MMAs per fp32-grade product (bf16x3 split)" % bf16[1]
         else:
             tpeak = peaks.get("fp64_tflops", 40.0)
             src = ("cuBLAS fp64 GEMM (DMMA) measured in this run" if "fp64_tflops" in peaks
                    else "nominal B200 fp64 tensor rate")
         return {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
                 "traffic": traffic, "traffic_source": traffic_src,
-                "kernel": ("dense_tf32_kernel / pot_tf32_kernel (tcgen05.mma kind::tf32, 3 MMAs per product)" if f32
+                "kernel": ("dense_tc_kernel (tcgen05.mma kind::f16, bf16x3 operands: 6 MMAs per product, TMEM accumulators)" if f32
                            else "dense_sample_kernel (mma.sync m8n8k4 f64 = DMMA)"),
                 "peak_source": src, "algorithmic_flops_per_leapfrog_step": fl, "launch_ms": launch_ms,
                 "hbm_gbs": achieved}

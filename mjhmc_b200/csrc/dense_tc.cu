@@ -28,6 +28,7 @@
 // to bar_done.  The accumulator is double-buffered in TMEM (the Gaussian alternates D0 / D1, ProductOfT keeps Y in
 // D0 and dEdX in D1), so the MMAs of product n+1 may overwrite nothing the epilogue of product n still reads.
 // Round 1's kernel was MMA -> epilogue -> MMA strictly serial (tensor pipe 29.7 % active).
+#include <cstdio>
 #include <cuda_bf16.h>
 #include "dense.h"
 
@@ -228,8 +229,20 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     const uint32_t idesc_k = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t idesc_mn = idesc_k | (1u << 16);
     const uint32_t a_addr = smem_u32(A0), b_addr = smem_u32(B0);
+    // descriptor pieces for the MMA warp: the 14-bit start address (16-byte units) of every plane is the low word,
+    // LBO / SBO / version the high part; a K step advances the start address by a constant
+    const uint64_t a_desc_hi = make_desc(0, kTcCoreColBytes, 128);
+    const uint64_t b_desc_hi_k = make_desc(0, 128, (uint32_t)ncores * 128u);            // K-major view: N = row, K = column
+    const uint64_t b_desc_hi_mn = make_desc(0, (uint32_t)ncores * 128u, 128);           // MN-major view: N = column, K = row
+    const uint32_t b_kstep_mn = (uint32_t)(2 * ncores * 128) >> 4;
+    uint32_t a_lo[3], b_lo[3];
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) { a_lo[pl] = ((a_addr + pl * a_plane) >> 4) & 0x3FFFu; b_lo[pl] = ((b_addr + pl * b_plane) >> 4) & 0x3FFFu; }
+    const bool leader = lane == 0;
 
-    const float eps = (float)p.eps, nhe = (float)(-p.eps / 2.0);
+    float eps = (float)p.eps, nhe = (float)(-p.eps / 2.0), neg_eps = nhe + nhe;
+    // pinned: ptxas otherwise re-derives these from the double in the constant bank inside the sweep (DMUL + F2F per use)
+    asm volatile("" : "+f"(eps), "+f"(nhe), "+f"(neg_eps));
     const int L = p.L, sampler = p.sampler;
     const bool mj = sampler == MJHMC_SAMPLER_MARKOV_JUMP;
     const int nprod = POT ? 2 * L + 2 : L + 1;     // products of one tile trajectory
@@ -242,6 +255,12 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     const long long r0 = p.n * (long long)blockIdx.x / gridDim.x, r1 = p.n * (long long)(blockIdx.x + 1) / gridDim.x;
 
     float x[kTcCPT][8], v[kTcCPT][8];
+#ifdef TCX_TIMING
+    long long tph[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
+#define TCX_MARK(k) { const long long tnow = clock64(); tph[k] += tnow - tlast; tlast = tnow; }
+#else
+#define TCX_MARK(k)
+#endif
 
     for (int it = 0; it < p.n_iter; ++it) {
         const unsigned long long attempt = p.attempt0 + (unsigned long long)it;
@@ -285,6 +304,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
             const int nflf = __syncthreads_count(mine && need);
             const int nrows = np + nflf;
 
+            TCX_MARK(0)
             // ---- my job: row m -> (particle, sign)
             const bool is_l = epi && m < np, is_flf = epi && m >= np && m < nrows;
             const int part = is_l ? m : (is_flf ? s_row_part[m] : 0);
@@ -307,6 +327,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                     }
                 }
                 float e_start = 0.0f, e_end = 0.0f;
+                TCX_MARK(1)
 
                 // ---- first A operand: the positions
 #pragma unroll
@@ -367,32 +388,59 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                     tc_fence_after();
                     const uint32_t dcol = tmem_base + my_lane + (POT ? 128u : ((pc & 1u) ? 128u : 0u));
                     ++pc;
+                    if (st > 0 && st < L) {
+                        // steps 1 .. L-1: the closing half kick of step st and the opening one of step st+1 are one
+                        // full kick, then the drift -- two FMAs per dim, then the bf16 split of the new positions
 #pragma unroll
-                    for (int c = 0; c < kTcCPT; ++c) {
-                        if (c < nchunks) {
-                            const int kc = 4 * c + q;
-                            if (kc < ncores) {
-                                float g[8];
-                                tmem_ld8(dcol + (uint32_t)(kc * 8), g);
+                        for (int c = 0; c < kTcCPT; ++c) {
+                            if (c < nchunks) {
+                                const int kc = 4 * c + q;
+                                if (kc < ncores) {
+                                    float g[8];
+                                    tmem_ld8(dcol + (uint32_t)(kc * 8), g);
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float gk = g[j];
-                                    float vv = v[c][j];
-                                    if (!POT) {
-                                        e_start += st == 0 ? x[c][j] * gk : 0.0f;      // E = x.(S x)/2
-                                        e_end += st == L ? x[c][j] * gk : 0.0f;
+                                    for (int j = 0; j < 8; ++j) {
+                                        v[c][j] = fmaf(neg_eps, g[j], v[c][j]);
+                                        x[c][j] = fmaf(eps, v[c][j], x[c][j]);
                                     }
-                                    vv += st > 0 ? nhe * gk : 0.0f;        // second half kick of step st
-                                    vv += st < L ? nhe * gk : 0.0f;        // first half kick of step st+1
-                                    x[c][j] += st < L ? eps * vv : 0.0f;   // drift of step st+1
-                                    v[c][j] = vv;
+                                    split3_store(x[c], A0, a_plane, a_row_offset(m, kc));
                                 }
-                                if (st < L) split3_store(x[c], A0, a_plane, a_row_offset(m, kc));
-                            }
-                            if (st < L) {
                                 fence_async_smem();
                                 tc_fence_before();
                                 mbar_arrive(&bar_chunk[c]);
+                            }
+                        }
+                    } else {
+                        // the two ends of the trajectory: energies, half kicks
+#pragma unroll
+                        for (int c = 0; c < kTcCPT; ++c) {
+                            if (c < nchunks) {
+                                const int kc = 4 * c + q;
+                                if (kc < ncores) {
+                                    float g[8];
+                                    tmem_ld8(dcol + (uint32_t)(kc * 8), g);
+                                    if (!POT) {
+                                        float e = 0.0f;                      // E = x.(S x)/2
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) e = fmaf(x[c][j], g[j], e);
+                                        if (st == 0) e_start += e;
+                                        if (st == L) e_end += e;
+                                    }
+                                    if (L > 0) {
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) v[c][j] = fmaf(nhe, g[j], v[c][j]);   // opening / closing half kick
+                                    }
+                                    if (st < L) {
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) x[c][j] = fmaf(eps, v[c][j], x[c][j]);
+                                        split3_store(x[c], A0, a_plane, a_row_offset(m, kc));
+                                    }
+                                }
+                                if (st < L) {
+                                    fence_async_smem();
+                                    tc_fence_before();
+                                    mbar_arrive(&bar_chunk[c]);
+                                }
                             }
                         }
                     }
@@ -407,30 +455,38 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                 s_red[0][q][m] = e_start + 0.5f * ev0;                          // EX + EV, hmc_state.py:80-84
                 s_red[1][q][m] = e_end + 0.5f * ev1;
             } else {
-                // ---- the MMA warp: chunk c of a product is issued as soon as its 512 writers have arrived
+                // ---- the MMA warp: chunk c of a product is issued as soon as its 512 writers have arrived.
+                // One elected lane issues; the descriptors are base + immediate (a single thread executes ~1
+                // instruction per 4 cycles: rebuilding six 64-bit descriptors per K step cost 250 cycles per MMA in
+                // tools/probe/tc_probe4.cu, against 56 for the MMA itself).
                 for (int prod = 0; prod < nprod; ++prod) {
                     const bool y_prod = POT && !(prod & 1);                      // Y = X W: B read MN-major (K = dims)
                     const uint32_t dacc = tmem_base + (POT ? (y_prod ? 0u : 128u) : ((pc & 1u) ? 128u : 0u));
+                    const uint32_t idesc = y_prod ? idesc_mn : idesc_k;
+                    const uint64_t bhi = y_prod ? b_desc_hi_mn : b_desc_hi_k;
+                    const uint32_t bstep = y_prod ? b_kstep_mn : 16u;            // descriptor address units (16 B) per K step
                     for (int c = 0; c < nchunks; ++c) {
                         mbar_wait(&bar_chunk[c], pc & 1u);
                         tc_fence_after();
-                        if (lane == 0) {
-                            const int kg1 = min(ksteps, 2 * c + 2);
-                            for (int kg = 2 * c; kg < kg1; ++kg) {
-                                uint64_t ad[3], bd[3];
+                        if (leader) {
 #pragma unroll
-                                for (int pl = 0; pl < 3; ++pl) {
-                                    ad[pl] = make_desc(a_addr + pl * a_plane + kg * 2 * kTcCoreColBytes, kTcCoreColBytes, 128);
-                                    bd[pl] = y_prod ? make_desc(b_addr + pl * b_plane + kg * 2 * ncores * 128, ncores * 128, 128)
-                                                    : make_desc(b_addr + pl * b_plane + kg * 256, 128, ncores * 128);
+                            for (int kk = 0; kk < 2; ++kk) {
+                                const int kg = 2 * c + kk;
+                                if (kg < ksteps) {
+                                    const uint32_t ao = (uint32_t)kg * 256u, bo = (uint32_t)kg * bstep;
+                                    const uint64_t a0d = a_desc_hi | (uint64_t)(a_lo[0] + ao), a1d = a_desc_hi | (uint64_t)(a_lo[1] + ao),
+                                                   a2d = a_desc_hi | (uint64_t)(a_lo[2] + ao);
+                                    const uint64_t b0d = bhi | (uint64_t)(b_lo[0] + bo), b1d = bhi | (uint64_t)(b_lo[1] + bo),
+                                                   b2d = bhi | (uint64_t)(b_lo[2] + bo);
+#ifndef TCX_NOMMA
+                                    umma_bf16(dacc, a0d, b0d, idesc, kg > 0 ? 1u : 0u);
+                                    umma_bf16(dacc, a0d, b1d, idesc, 1u);
+                                    umma_bf16(dacc, a1d, b0d, idesc, 1u);
+                                    umma_bf16(dacc, a1d, b1d, idesc, 1u);
+                                    umma_bf16(dacc, a0d, b2d, idesc, 1u);
+                                    umma_bf16(dacc, a2d, b0d, idesc, 1u);
+#endif
                                 }
-                                const uint32_t idesc = y_prod ? idesc_mn : idesc_k;
-                                umma_bf16(dacc, ad[0], bd[0], idesc, kg > 0 ? 1u : 0u);
-                                umma_bf16(dacc, ad[0], bd[1], idesc, 1u);
-                                umma_bf16(dacc, ad[1], bd[0], idesc, 1u);
-                                umma_bf16(dacc, ad[1], bd[1], idesc, 1u);
-                                umma_bf16(dacc, ad[0], bd[2], idesc, 1u);
-                                umma_bf16(dacc, ad[2], bd[0], idesc, 1u);
                             }
                             if (c == nchunks - 1) umma_commit(&bar_done);
                         }
@@ -439,7 +495,9 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                     ++pc;
                 }
             }
+            TCX_MARK(2)
             __syncthreads();
+            TCX_MARK(3)
 
             // ---- decision by the lead thread of each L job (same device code as the register-resident kernel)
             unsigned int take = 0, flip = 0, refresh = 0, choice = 0, ok = 0;
@@ -496,12 +554,33 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                 }
             }
             __syncthreads();
+            TCX_MARK(4)
 
             // ---- apply: my slice of my particle's new state goes to the output arrays
             if (is_l) {
                 const unsigned int code = s_code[m];
                 const unsigned int tk = code & 3u;
                 const bool fp = code & 4u, rf = code & 8u, okk = code & 16u;
+                // a particle that did not take the trajectory keeps its state: fetch it in one batch of independent
+                // loads (load -> store pairs element by element serialise on the memory latency: Xout may alias Xin)
+                if (!(okk && tk)) {
+#pragma unroll
+                    for (int c = 0; c < kTcCPT; ++c) {
+                        const int kc = 4 * c + q;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int k = kc * 8 + j;
+                            if (k < d) { x[c][j] = Xc[(long long)k * p.ld + i]; v[c][j] = Vc[(long long)k * p.ld + i]; }
+                        }
+                    }
+                } else if (tk == 2) {
+#pragma unroll
+                    for (int c = 0; c < kTcCPT; ++c)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[c][j] = -v[c][j];
+                }
+                const float vs = (okk && fp) ? -1.0f : 1.0f;
+                const float rk = (float)p.r_keep, rm = (float)p.r_mix;
 #pragma unroll
                 for (int c = 0; c < kTcCPT; ++c) {
                     const int kc = 4 * c + q;
@@ -516,14 +595,11 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                                 const int k = k0 + e, j = 2 * jj + e;
                                 if (k < d) {
                                     const long long o = (long long)k * p.ld + i;
-                                    float xn, vn;
-                                    if (okk && tk) { xn = x[c][j]; vn = tk == 1 ? v[c][j] : -v[c][j]; }
-                                    else { xn = Xc[o]; vn = Vc[o]; }
-                                    if (okk && fp) vn = -vn;
-                                    if (okk && rf) vn = vn * (float)p.r_keep + (float)z[e] * (float)p.r_mix;   // hmc_state.py:126
-                                    Xo[o] = xn;
+                                    float vn = vs * v[c][j];
+                                    if (okk && rf) vn = vn * rk + (float)z[e] * rm;   // hmc_state.py:126
+                                    Xo[o] = x[c][j];
                                     Vo[o] = vn;
-                                    if (okk && p.samples) ((float*)p.samples)[(long long)k * p.s_stride_k + (long long)it * p.s_stride_it + i] = xn;
+                                    if (okk && p.samples) ((float*)p.samples)[(long long)k * p.s_stride_k + (long long)it * p.s_stride_it + i] = x[c][j];
                                 }
                             }
                         }
@@ -531,6 +607,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                 }
             }
             __syncthreads();                       // the tables, s_red and the A planes are reused by the next tile
+            TCX_MARK(5)
             cur += np;
         }
     }
@@ -546,6 +623,10 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
         }
     }
 
+#ifdef TCX_TIMING
+    if (blockIdx.x == 0 && (tid == 0 || tid == 130 || tid == 300 || tid == 512))
+        printf("tid %d: plan %lld load %lld traj %lld sync %lld decide %lld apply %lld\n", tid, tph[0], tph[1], tph[2], tph[3], tph[4], tph[5]);
+#endif
     // ---- teardown
     tc_fence_before();
     __syncthreads();
