@@ -89,6 +89,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// one lane of a converged warp (elect.sync): keeps the control flow warp-uniform, so the descriptor arithmetic of the
+// MMA warp stays in uniform registers instead of being moved there (R2UR) in front of every UTCHMMA
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "elect.sync _|P1, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -238,7 +250,6 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     uint32_t a_lo[3], b_lo[3];
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) { a_lo[pl] = ((a_addr + pl * a_plane) >> 4) & 0x3FFFu; b_lo[pl] = ((b_addr + pl * b_plane) >> 4) & 0x3FFFu; }
-    const bool leader = lane == 0;
 
     float eps = (float)p.eps, nhe = (float)(-p.eps / 2.0), neg_eps = nhe + nhe;
     // pinned: ptxas otherwise re-derives these from the double in the constant bank inside the sweep (DMUL + F2F per use)
@@ -257,9 +268,14 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     float x[kTcCPT][8], v[kTcCPT][8];
 #ifdef TCX_TIMING
     long long tph[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
+    long long tw[6] = {0, 0, 0, 0, 0, 0};          // epilogue: [0] wait bar_done, [1] work; MMA warp: [0..3] wait chunk c, [4] issue
+#define TCX_T0 const long long tq0 = clock64();
+#define TCX_ACC(k) tw[k] += clock64() - tq0;
 #define TCX_MARK(k) { const long long tnow = clock64(); tph[k] += tnow - tlast; tlast = tnow; }
 #else
 #define TCX_MARK(k)
+#define TCX_T0
+#define TCX_ACC(k)
 #endif
 
     for (int it = 0; it < p.n_iter; ++it) {
@@ -384,7 +400,9 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                         }
                     }
                     // ---- gradient sweep: kick, drift, next positions
+                    { TCX_T0
                     mbar_wait(&bar_done, pc & 1u);
+                    TCX_ACC(0) }
                     tc_fence_after();
                     const uint32_t dcol = tmem_base + my_lane + (POT ? 128u : ((pc & 1u) ? 128u : 0u));
                     ++pc;
@@ -466,9 +484,12 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                     const uint64_t bhi = y_prod ? b_desc_hi_mn : b_desc_hi_k;
                     const uint32_t bstep = y_prod ? b_kstep_mn : 16u;            // descriptor address units (16 B) per K step
                     for (int c = 0; c < nchunks; ++c) {
+                        { TCX_T0
                         mbar_wait(&bar_chunk[c], pc & 1u);
+                        TCX_ACC(c) }
                         tc_fence_after();
-                        if (leader) {
+                        TCX_T0
+                        if (elect_one()) {
 #pragma unroll
                             for (int kk = 0; kk < 2; ++kk) {
                                 const int kg = 2 * c + kk;
@@ -491,6 +512,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                             if (c == nchunks - 1) umma_commit(&bar_done);
                         }
                         __syncwarp();
+                        TCX_ACC(4)
                     }
                     ++pc;
                 }
@@ -625,7 +647,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
 
 #ifdef TCX_TIMING
     if (blockIdx.x == 0 && (tid == 0 || tid == 130 || tid == 300 || tid == 512))
-        printf("tid %d: plan %lld load %lld traj %lld sync %lld decide %lld apply %lld\n", tid, tph[0], tph[1], tph[2], tph[3], tph[4], tph[5]);
+        printf("tid %d: plan %lld load %lld traj %lld sync %lld decide %lld apply %lld | w0 %lld w1 %lld w2 %lld w3 %lld issue %lld\n", tid, tph[0], tph[1], tph[2], tph[3], tph[4], tph[5], tw[0], tw[1], tw[2], tw[3], tw[4]);
 #endif
     // ---- teardown
     tc_fence_before();
