@@ -99,9 +99,10 @@ WORKLOADS = {
                                       epsilon=0.0010000000474974513, beta=0.009999999776482582, L=1, iters=1,
                                       source="search/control_log_gauss/params.json; reference default diagonal J; streaming kernel"),
     # configs[4]: Funnel 10-d ContinuousTimeHMC with the autocorrelation / ESS statistics reduced across GPUs
-    "funnel10d_cthmc_ess": dict(dist="Funnel", ndims=10, n=1_000_000, sampler="ContinuousTimeHMC",
-                                epsilon=0.1, beta=0.5, L=10, iters=256, ess=dict(n_lags=128),
-                                source="search/MJHMC_funnel/config.json midpoints; ESS from fft_autocor over 256 recorded steps"),
+    "funnel10d_cthmc_ess": dict(dist="Funnel", scale=1.0, ndims=10, n=4_000_000, sampler="ContinuousTimeHMC",
+                                epsilon=0.2, beta=0.9, L=25, iters=16, ess=dict(T=1024, n_lags=1024, block=500_000),
+                                source="inside the ranges of search/MJHMC_funnel/config.json, where the fft_autocor curve "
+                                       "crosses zero inside the window (lag ~300); ESS from 1024 recorded steps"),
 }
 DEFAULT_WORKLOAD = "roughwell2d_mjhmc"
 DTYPE = "float64"          # the reference's arithmetic
@@ -153,7 +154,7 @@ def _oracle_energy(w):
     if w["dist"] == "DiagGaussian":
         return orc.GaussianEnergy.log_conditioned(w["ndims"], w.get("log_cond", 1))
     if w["dist"] == "Funnel":
-        return orc.FunnelEnergy(3.0)
+        return orc.FunnelEnergy(w.get("scale", 3.0))
     if w["dist"] == "GaussianRot":
         return orc.GaussianEnergy(_rotated_J(w["ndims"]))
     if w["dist"] == "ProductOfT":
@@ -181,7 +182,7 @@ def _init_cloud(w, n, seed):
     if w["dist"] == "RoughWell":
         X = 100 * rs.randn(d, n)                               # distributions.py:308
     elif w["dist"] == "Funnel":
-        x0 = rs.normal(scale=3.0, size=(1, n))
+        x0 = rs.normal(scale=w.get("scale", 3.0), size=(1, n))
         X = np.vstack((x0, rs.normal(scale=np.exp(x0 / 2.), size=(d - 1, n))))
     elif w["dist"] == "GaussianRot":
         wv, Q = np.linalg.eigh(_rotated_J(d))
@@ -289,7 +290,7 @@ def _oracle_ess_worker(args):
     s = orc.OracleSampler(w["sampler"], _oracle_energy(w), X, V=V, epsilon=w["epsilon"], beta=w["beta"],
                           num_leapfrog_steps=w["L"], draws=orc.FastNumpyDraws(seed), resample=False)
     t0 = time.perf_counter()
-    S = s.sample(w["iters"], preserve_order=True)                      # (d, n, T)
+    S = s.sample(w["ess"]["T"], preserve_order=True)                   # (d, n, T)
     t_sample = time.perf_counter() - t0
     f = np.fft.fft(S, axis=-1)
     ac = np.real(np.sum(np.fft.ifft(f * np.conj(f), axis=-1), axis=(0, 1)))   # un-normalised, summed over dims and particles
@@ -310,7 +311,7 @@ def run_reference_ess(w, n_per_core=2000):
     t = max(r[2] for r in res)
     n = n_per_core * cores
     return dict(ess_per_chain=ess, chains=n, seconds=t, ess_per_s=ess * n / t, cores=cores, kind="port",
-                sample="%d chains (%d per core x %d cores), %d recorded steps each" % (n, n_per_core, cores, w["iters"]))
+                sample="%d chains (%d per core x %d cores), %d recorded steps each" % (n, n_per_core, cores, w["ess"]["T"]))
 
 
 def _ess_from_curve(ac, T):
@@ -334,7 +335,7 @@ def _device_cloud(w, n, seed, dev, tdtype):
     if w["dist"] == "RoughWell":
         X = 100 * rn(d, n)
     elif w["dist"] == "Funnel":
-        x0 = 3.0 * rn(1, n)
+        x0 = w.get("scale", 3.0) * rn(1, n)
         X = torch.cat((x0, torch.exp(x0 / 2.) * rn(d - 1, n)), dim=0)
     elif w["dist"] == "GaussianRot":
         wv, Q = np.linalg.eigh(_rotated_J(d))
@@ -358,7 +359,7 @@ def make_sampler(w, rank, dtype=None, seed=2024, n=None, device_init=None):
     elif w["dist"] == "DiagGaussian":
         dist = D.Gaussian(ndims=d, nbatch=8, log_conditioning=w.get("log_cond", 1))
     elif w["dist"] == "Funnel":
-        dist = D.Funnel(scale=3.0, ndims=d, nbatch=8)
+        dist = D.Funnel(scale=w.get("scale", 3.0), ndims=d, nbatch=8)
     elif w["dist"] == "GaussianRot":
         dist = D.Gaussian(ndims=d, nbatch=8, J=_rotated_J(d))
     elif w["dist"] == "ProductOfT":
@@ -562,34 +563,59 @@ def roofline_of(ctx, m, peaks):
 
 
 def measure_ess(ctx, m, cpu=False):
-    """ESS/s (BASELINE metric iii): T recorded steps, per-GPU autocorrelation sums, one all-reduce of float64[n_lags]."""
+    """ESS/s (BASELINE metric iii): T recorded steps of every chain, per-GPU autocorrelation sums through the FFT kernel
+    (csrc/autocorr_fft.cu: what misc/autocor.py:37-49 does), one all-reduce of float64[n_lags] over NCCL.  The chains are
+    independent, so the cloud is walked in particle blocks whose recorded samples (ndims x T x block) fit in HBM."""
     torch = ctx.torch
     from mjhmc_b200 import parallel
-    w, sampler = m["w"], m["sampler"]
-    iters, n_lags = w["iters"], w["ess"]["n_lags"]
+    w = m["w"]
+    T, n_lags, block = w["ess"]["T"], w["ess"]["n_lags"], w["ess"]["block"]
+    for key in ("sampler", "dist", "X0", "V0"):
+        m.pop(key, None)
+    torch.cuda.empty_cache()
+    n_total = m["n"]
+    part = torch.zeros(n_lags, dtype=torch.float64, device=ctx.dev)
+    t_s = t_a = 0.0
+    done = 0
+    blk = 0
+    while done < n_total:
+        nb = min(block, n_total - done)
+        sampler, _, _, _ = make_sampler(dict(w, n=nb), ctx.rank * 64 + blk, n=nb, device_init=ctx.dev)
+        sampler.sample_device(4)                                            # warm the block's launch path
+        ctx.barrier()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        S = sampler.sample_device(T)
+        e1.record()
+        part += parallel.autocorr_partial(S, n_lags=n_lags, circular=True)
+        e2.record()
+        torch.cuda.synchronize()
+        t_s += e0.elapsed_time(e1)
+        t_a += e1.elapsed_time(e2)
+        del S, sampler
+        torch.cuda.empty_cache()
+        done += nb
+        blk += 1
     ctx.barrier()
-    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    e0.record()
-    S = sampler.sample_device(iters)
-    e1.record()
-    part = parallel.autocorr_partial(S, n_lags=n_lags, circular=True)
+    e3, e4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e3.record()
     if ctx.world > 1:
-        ctx.dist.all_reduce(part)                                   # the statistics "gathered over NVLink"
-    e2.record()
+        ctx.dist.all_reduce(part)                                           # the statistics "gathered over NVLink"
+    e4.record()
     ctx.barrier()
+    t_s, t_a, t_r = ctx.max_f(t_s, t_a, e3.elapsed_time(e4))
     ac = part.double().cpu().numpy()
     ac = ac / ac[0]
-    t_s, t_a = ctx.max_f(e0.elapsed_time(e1), e1.elapsed_time(e2))
-    ess_chain = _ess_from_curve(ac, iters)
+    ess_chain = _ess_from_curve(ac, T)
     crossed = bool(np.any(ac[1:] < 0))
-    ess = {"definition": "T / (1 + 2 sum_{tau>=1}^{first rho<0} rho_tau) on the circular fft_autocor curve (autocor.py:37-49), "
-                         "first %d lags" % n_lags,
-           "T": iters, "n_lags": n_lags, "chains": m["n"] * ctx.world, "ess_per_chain": ess_chain,
-           "sampling_ms": t_s, "autocorr_allreduce_ms": t_a, "autocorr_share_of_sampling": t_a / t_s,
-           "ess_per_s": ess_chain * m["n"] * ctx.world / ((t_s + t_a) * 1e-3), "rho_1": float(ac[1]),
+    ess = {"definition": "T / (1 + 2 sum_{tau>=1}^{first rho<0} rho_tau) on the circular fft_autocor curve (autocor.py:37-49); "
+                         "the reference defines no ESS (its figure of merit is a fitted decay, search/objective.py:121-185)",
+           "T": T, "n_lags": n_lags, "chains": n_total * ctx.world, "blocks_per_gpu": blk, "ess_per_chain": ess_chain,
+           "sampling_ms": t_s, "autocorr_ms": t_a, "allreduce_ms": t_r, "autocorr_share_of_sampling": t_a / t_s,
+           "ess_per_s": ess_chain * n_total * ctx.world / ((t_s + t_a + t_r) * 1e-3), "rho_1": float(ac[1]),
            "rho_last": float(ac[-1]), "rho_crosses_zero_inside_window": crossed,
-           "first_negative_lag": int(np.argmax(ac < 0)) if crossed else None}
-    del S, part
+           "first_negative_lag": int(np.argmax(ac < 0)) if crossed else None,
+           "autocorr_kernel": "autocorr_fft_kernel (batched radix-4 forward FFTs in shared memory + one inverse transform)"}
     if cpu:
         ess["cpu"] = run_reference_ess(w)
     return ess
@@ -619,7 +645,7 @@ def measure_e2e(ctx, m, steps):
     Xh = torch.as_tensor(m["X0"]).pin_memory()                  # host inputs live in pinned memory
     Vh = torch.as_tensor(m["V0"]).pin_memory()
     e2e_steps = max(1, min(steps, 5))
-    e2e_iters = 8 if w.get("ess") else w["iters"]
+    e2e_iters = w["iters"]
 
     def e2e_step():
         sampler.state = HMCState.from_buffers(sampler, Xh, Vh)   # H2D from pinned memory at the next launch
@@ -679,9 +705,9 @@ def run_b200(args, w):
     peaks = measured_tensor_peaks(ctx)
     clocks = ClockSampler(ctx.local_rank) if rank == 0 else None
     m = measure_device(ctx, args.workload, w, args.steps, args.warmup, n=n_main, host_init=True, clocks=clocks)
-    ess = measure_ess(ctx, m, cpu=(rank == 0 and world == 1 and not args.no_cpu_baseline)) if w.get("ess") else None
     e2e = measure_e2e(ctx, m, args.steps)
     main_summary = summarise(ctx, m, peaks)
+    ess = measure_ess(ctx, m, cpu=(rank == 0 and world == 1 and not args.no_cpu_baseline)) if w.get("ess") else None
     clk = m["clk"]
 
     # ---- strong scaling of the same workload (the cloud of ONE GPU's worth split over the ranks), N > 1 only

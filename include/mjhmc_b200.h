@@ -236,6 +236,15 @@ int mjhmc_resample(int32_t dtype, int32_t ndims, const double *dwell, int64_t m,
 int mjhmc_autocorr(int32_t dtype, int32_t ndims, const void *samples, int64_t stride_k, int64_t stride_it,
                    int64_t n, int32_t T, int32_t n_lags, int32_t circular, double *ac, void *stream);
 
+/* The same circular sums as mjhmc_autocorr(circular = 1) the way the reference computes them (misc/autocor.py:37-49:
+ * FFT along time, |.|^2, inverse FFT): one forward FFT per pair of series, the power spectrum summed over all series,
+ * ONE inverse transform per call -- O(T log T) per series instead of O(T n_lags).  T must be a power of two,
+ * 16 <= T <= 4096 (mjhmc_autocorr_fft_scratch_bytes returns -1 otherwise); n_lags <= T.  ac += sums (not normalised).
+ * scratch: device buffer of mjhmc_autocorr_fft_scratch_bytes(T) bytes. */
+int64_t mjhmc_autocorr_fft_scratch_bytes(int32_t T);
+int mjhmc_autocorr_fft(int32_t dtype, int32_t ndims, const void *samples, int64_t stride_k, int64_t stride_it, int64_t n,
+                       int32_t T, int32_t n_lags, double *ac, void *scratch, void *stream);
+
 /* Replaces the Welford loop of online_variance (misc/gen_mj_init.py:76-98) for one chunk of samples:
  * out[0] += sum x, out[1] += sum x^2 over `count` contiguous elements (double accumulation). */
 int mjhmc_moments(int32_t dtype, const void *x, int64_t count, double *out, void *stream);

@@ -87,6 +87,9 @@ SYMBOLS = {
                                  C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mjhmc_autocorr": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                  C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mjhmc_autocorr_fft_scratch_bytes": (C.c_int64, [C.c_int32]),
+    "mjhmc_autocorr_fft": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mjhmc_moments": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
 }
 

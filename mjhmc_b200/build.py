@@ -27,7 +27,7 @@ STREAM_DTS = [2, 4, 6, 8, 10, 13, 16]     # dims per thread of the streaming ker
 
 def _units():
     units = []
-    for name in ("api", "unfused", "analysis", "dense", "dense_tc", "stream"):
+    for name in ("api", "unfused", "analysis", "autocorr_fft", "dense", "dense_tc", "stream"):
         units.append((name, os.path.join(CSRC, name + ".cu"), []))
     for tname, ctype in (("f64", "double"), ("f32", "float")):
         for g, (da, db) in enumerate(DIM_GROUPS):

@@ -325,6 +325,18 @@ int mjhmc_autocorr(int32_t dtype, int32_t ndims, const void* samples, int64_t st
                                  (cudaStream_t)stream), "autocorr");
 }
 
+int64_t mjhmc_autocorr_fft_scratch_bytes(int32_t T) { return autocorr_fft_supported(T, 1) ? autocorr_fft_scratch_bytes(T) : -1; }
+
+int mjhmc_autocorr_fft(int32_t dtype, int32_t ndims, const void* samples, int64_t stride_k, int64_t stride_it, int64_t n,
+                       int32_t T, int32_t n_lags, double* ac, void* scratch, void* stream) {
+    if (dtype != MJHMC_F32 && dtype != MJHMC_F64) return fail("bad dtype");
+    if (n < 0 || T < 0 || n_lags < 0 || n_lags > T || ndims <= 0) return fail("bad sizes");
+    if (!autocorr_fft_supported(T, 1)) return fail("the FFT autocorrelation needs T = 2^m, 16 <= T <= 4096 (use mjhmc_autocorr)");
+    if (n && n_lags && (!samples || !ac || !scratch)) return fail("NULL argument");
+    return check(launch_autocorr_fft(dtype, ndims, samples, stride_k, stride_it, n, T, n_lags, ac, (double*)scratch,
+                                     (cudaStream_t)stream), "autocorr_fft");
+}
+
 int mjhmc_moments(int32_t dtype, const void* x, int64_t count, double* out, void* stream) {
     if (dtype != MJHMC_F32 && dtype != MJHMC_F64) return fail("bad dtype");
     if (count < 0) return fail("bad count");

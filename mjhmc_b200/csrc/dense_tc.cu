@@ -21,8 +21,8 @@
 // fit beside the particle tile in 227 KB; three bf16 planes of ONE copy do (75 KB), at the same MMA cycle count.
 //
 // Pipeline inside a tile.  16 epilogue warps (4 threads per row: thread (m, q) owns the 8-wide core columns
-// q, 4+q, 8+q, 12+q of row m -- positions and momenta of those dims stay in its registers) and one MMA warp.
-// A product is cut into K chunks of 32 columns.  The epilogue threads write chunk c of the next A operand
+// of row m listed by tc_core() -- positions and momenta of those dims stay in its registers) and one MMA warp.
+// A product is cut into K chunks of 16 / 32 columns.  The epilogue threads write chunk c of the next A operand
 // (positions after the drift, or G for ProductOfT), fence, and arrive on bar_chunk[c]; the MMA warp waits for
 // chunk c only and issues its 12 MMAs while the epilogue threads work on chunk c+1; after the last chunk it commits
 // to bar_done.  The accumulator is double-buffered in TMEM (the Gaussian alternates D0 / D1, ProductOfT keeps Y in
@@ -134,6 +134,11 @@ __device__ __forceinline__ uint32_t a_row_offset(int m, int kc) {
     return (uint32_t)kc * kTcCoreColBytes + (uint32_t)(m >> 3) * 128u + (uint32_t)(m & 7) * 16u;
 }
 
+// Core column (8 dims) that thread slice q owns in K chunk c.  The first chunk is ONE K step (cores 0, 1: slices 0 and
+// 1 only), the others two (cores 4c-2 .. 4c+1): the MMA warp can start a product after half the usual wait, and
+// every core 0 .. 13 has exactly one owner.  kTcMaxP / 8 = "none" (fails every bound check).
+__device__ __forceinline__ int tc_core(int c, int q) { return c ? 4 * c - 2 + q : (q < 2 ? q : kTcMaxP / 8); }
+
 // x = x0 + x1 + x2 with bf16 parts (round to nearest; the remainders are exact): 8 values -> one 16-byte row per plane
 __device__ __forceinline__ void split3_store(const float (&x)[8], uint8_t* plane0, uint32_t plane_bytes, uint32_t off) {
     uint32_t p0[4], p1[4], p2[4];
@@ -200,12 +205,13 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     __shared__ int s_flf_row[kTcRows];                // particle of the chunk -> row of its FLF job, -1 = none
     __shared__ int s_row_part[kTcRows];               // FLF row -> particle of the chunk
     __shared__ unsigned int s_code[kTcRows];          // decision of each particle, broadcast to its 4 threads
+    __shared__ int s_nr, s_rlist[kTcRows];            // particles of the tile whose momentum is refreshed (R moves)
 
     const int d = p.d;
     const int P = ((d + 15) >> 4) << 4;            // padded dims (= experts): N of the MMAs and K in steps of 16
     const int ncores = P >> 3;
     const int ksteps = P >> 4;
-    const int nchunks = (ksteps + 1) >> 1;
+    const int nchunks = (ksteps + 2) >> 1;         // K chunks of a product: steps [0,1), [1,3), [3,5), [5,7)
     const uint32_t a_plane = (uint32_t)ncores * kTcCoreColBytes;
     const uint32_t b_plane = (uint32_t)ncores * ncores * 128u;
     const uint32_t ws_bytes = 3u * b_plane + (POT ? (uint32_t)(kTcTabs * P * 4) : 0u);
@@ -266,6 +272,13 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     const long long r0 = p.n * (long long)blockIdx.x / gridDim.x, r1 = p.n * (long long)(blockIdx.x + 1) / gridDim.x;
 
     float x[kTcCPT][8], v[kTcCPT][8];
+#ifdef TCX_TRACE
+    __shared__ long long s_ev[12][16];
+    int tile_no = 0;
+#define TCX_EV(prod, slot) if (blockIdx.x == 0 && tile_no == 3 && (prod) >= 4 && (prod) < 16 && (tid == 0 || tid == 512)) s_ev[(prod) - 4][slot] = clock64();
+#else
+#define TCX_EV(prod, slot)
+#endif
 #ifdef TCX_TIMING
     long long tph[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
     long long tw[6] = {0, 0, 0, 0, 0, 0};          // epilogue: [0] wait bar_done, [1] work; MMA warp: [0..3] wait chunk c, [4] issue
@@ -304,6 +317,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                 }
                 if (lane == 31) s_wsum[warp] = incl;
             }
+            if (tid == 0) s_nr = 0;
             __syncthreads();
             if (tid < kTcRows) {
                 for (int w = 0; w < warp; ++w) incl += s_wsum[w];
@@ -333,7 +347,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                 float ev0 = 0.0f;
 #pragma unroll
                 for (int c = 0; c < kTcCPT; ++c) {
-                    const int kc = 4 * c + q;
+                    const int kc = tc_core(c, q);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int k = kc * 8 + j;
@@ -349,7 +363,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
 #pragma unroll
                 for (int c = 0; c < kTcCPT; ++c) {
                     if (c < nchunks) {
-                        const int kc = 4 * c + q;
+                        const int kc = tc_core(c, q);
                         if (kc < ncores) split3_store(x[c], A0, a_plane, a_row_offset(m, kc));
                         fence_async_smem();
                         tc_fence_before();
@@ -361,12 +375,13 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                     if (POT) {
                         // ---- phase 1: Y = X W + b  ->  G (and the energy at the two ends of the trajectory)
                         mbar_wait(&bar_done, pc & 1u);
+                        TCX_EV(2 * st, 0)
                         tc_fence_after();
                         ++pc;
 #pragma unroll
                         for (int c = 0; c < kTcCPT; ++c) {
                             if (c < nchunks) {
-                                const int kc = 4 * c + q;
+                                const int kc = tc_core(c, q);
                                 if (kc < ncores) {
                                     float y[8];
                                     tmem_ld8(tmem_base + my_lane + (uint32_t)(kc * 8), y);
@@ -396,6 +411,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                                 fence_async_smem();
                                 tc_fence_before();
                                 mbar_arrive(&bar_chunk[c]);
+                                TCX_EV(2 * st, 1 + c)
                             }
                         }
                     }
@@ -403,6 +419,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                     { TCX_T0
                     mbar_wait(&bar_done, pc & 1u);
                     TCX_ACC(0) }
+                    TCX_EV(POT ? 2 * st + 1 : st, 0)
                     tc_fence_after();
                     const uint32_t dcol = tmem_base + my_lane + (POT ? 128u : ((pc & 1u) ? 128u : 0u));
                     ++pc;
@@ -412,20 +429,30 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
 #pragma unroll
                         for (int c = 0; c < kTcCPT; ++c) {
                             if (c < nchunks) {
-                                const int kc = 4 * c + q;
+                                const int kc = tc_core(c, q);
                                 if (kc < ncores) {
                                     float g[8];
+#ifndef TCX_NOLD
                                     tmem_ld8(dcol + (uint32_t)(kc * 8), g);
+#else
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) g[j] = x[c][j] * 1e-3f;
+#endif
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) {
                                         v[c][j] = fmaf(neg_eps, g[j], v[c][j]);
                                         x[c][j] = fmaf(eps, v[c][j], x[c][j]);
                                     }
+#ifndef TCX_NOSTORE
                                     split3_store(x[c], A0, a_plane, a_row_offset(m, kc));
+#endif
                                 }
+#ifndef TCX_NOFENCE
                                 fence_async_smem();
+#endif
                                 tc_fence_before();
                                 mbar_arrive(&bar_chunk[c]);
+                                TCX_EV(POT ? 2 * st + 1 : st, 1 + c)
                             }
                         }
                     } else {
@@ -433,7 +460,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
 #pragma unroll
                         for (int c = 0; c < kTcCPT; ++c) {
                             if (c < nchunks) {
-                                const int kc = 4 * c + q;
+                                const int kc = tc_core(c, q);
                                 if (kc < ncores) {
                                     float g[8];
                                     tmem_ld8(dcol + (uint32_t)(kc * 8), g);
@@ -487,13 +514,14 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                         { TCX_T0
                         mbar_wait(&bar_chunk[c], pc & 1u);
                         TCX_ACC(c) }
+                        TCX_EV(prod - 1, 5 + c)
                         tc_fence_after();
                         TCX_T0
                         if (elect_one()) {
 #pragma unroll
                             for (int kk = 0; kk < 2; ++kk) {
-                                const int kg = 2 * c + kk;
-                                if (kg < ksteps) {
+                                const int kg = 2 * c - 1 + kk;
+                                if (kg >= 0 && kg < ksteps) {
                                     const uint32_t ao = (uint32_t)kg * 256u, bo = (uint32_t)kg * bstep;
                                     const uint64_t a0d = a_desc_hi | (uint64_t)(a_lo[0] + ao), a1d = a_desc_hi | (uint64_t)(a_lo[1] + ao),
                                                    a2d = a_desc_hi | (uint64_t)(a_lo[2] + ao);
@@ -512,6 +540,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                             if (c == nchunks - 1) umma_commit(&bar_done);
                         }
                         __syncwarp();
+                        TCX_EV(prod - 1, 9 + c)
                         TCX_ACC(4)
                     }
                     ++pc;
@@ -569,6 +598,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                     n_l += (acc && fl); n_f += (fl && !acc); n_fl += (acc && !fl); n_r += refresh;
                 }
                 s_code[tid] = take | (flip << 2) | (refresh << 3) | (ok << 4);
+                if (ok && refresh) s_rlist[atomicAdd(&s_nr, 1)] = tid;
                 if (ok) {
                     if (p.dwell) p.dwell[(long long)it * p.n + cur + tid] = dwell;
                     if (p.choice) p.choice[(long long)it * p.n + cur + tid] = (uint8_t)choice;
@@ -582,13 +612,13 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
             if (is_l) {
                 const unsigned int code = s_code[m];
                 const unsigned int tk = code & 3u;
-                const bool fp = code & 4u, rf = code & 8u, okk = code & 16u;
+                const bool fp = code & 4u, okk = code & 16u;
                 // a particle that did not take the trajectory keeps its state: fetch it in one batch of independent
                 // loads (load -> store pairs element by element serialise on the memory latency: Xout may alias Xin)
                 if (!(okk && tk)) {
 #pragma unroll
                     for (int c = 0; c < kTcCPT; ++c) {
-                        const int kc = 4 * c + q;
+                        const int kc = tc_core(c, q);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int k = kc * 8 + j;
@@ -602,34 +632,53 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                         for (int j = 0; j < 8; ++j) v[c][j] = -v[c][j];
                 }
                 const float vs = (okk && fp) ? -1.0f : 1.0f;
-                const float rk = (float)p.r_keep, rm = (float)p.r_mix;
 #pragma unroll
                 for (int c = 0; c < kTcCPT; ++c) {
-                    const int kc = 4 * c + q;
+                    const int kc = tc_core(c, q);
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int k0 = kc * 8 + 2 * jj;                     // dims k0, k0+1 share one Box-Muller pair
-                        if (k0 < d) {
-                            double z[2] = {0.0, 0.0};
-                            if (okk && rf) normal_pair(p, i, attempt, k0 >> 1, d, z[0], z[1]);
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                const int k = k0 + e, j = 2 * jj + e;
-                                if (k < d) {
-                                    const long long o = (long long)k * p.ld + i;
-                                    float vn = vs * v[c][j];
-                                    if (okk && rf) vn = vn * rk + (float)z[e] * rm;   // hmc_state.py:126
-                                    Xo[o] = x[c][j];
-                                    Vo[o] = vn;
-                                    if (okk && p.samples) ((float*)p.samples)[(long long)k * p.s_stride_k + (long long)it * p.s_stride_it + i] = x[c][j];
-                                }
-                            }
+                    for (int j = 0; j < 8; ++j) {
+                        const int k = kc * 8 + j;
+                        if (k < d) {
+                            const long long o = (long long)k * p.ld + i;
+                            Xo[o] = x[c][j];
+                            Vo[o] = vs * v[c][j];
+                            if (okk && p.samples) ((float*)p.samples)[(long long)k * p.s_stride_k + (long long)it * p.s_stride_it + i] = x[c][j];
                         }
+                    }
+                }
+            }
+            // ---- momentum refresh (hmc_state.py:121-129) of the R movers: all threads share the Box-Muller pairs of the
+            // few refreshed particles of the tile (one thread per particle slice would run the 16 pairs of its slice in
+            // warps where a single lane has an R move)
+            if (s_nr > 0) {
+                const float rk = (float)p.r_keep, rm = (float)p.r_mix;
+                __syncthreads();                                                   // after the momenta written above (partial refresh reads them)
+                const int npairs = (d + 1) >> 1, njobs = s_nr * npairs;
+                for (int job = tid; job < njobs; job += kTcThreads) {
+                    const int r = job / npairs, pr = job - r * npairs;
+                    const long long ip = cur + s_rlist[r];
+                    double z0, z1;
+                    normal_pair(p, ip, attempt, pr, d, z0, z1);
+                    const long long o0 = (long long)(2 * pr) * p.ld + ip;
+                    Vo[o0] = (rk != 0.0f ? Vo[o0] * rk : 0.0f) + (float)z0 * rm;  // hmc_state.py:126
+                    if (2 * pr + 1 < d) {
+                        const long long o1 = o0 + p.ld;
+                        Vo[o1] = (rk != 0.0f ? Vo[o1] * rk : 0.0f) + (float)z1 * rm;
                     }
                 }
             }
             __syncthreads();                       // the tables, s_red and the A planes are reused by the next tile
             TCX_MARK(5)
+#ifdef TCX_TRACE
+            if (blockIdx.x == 0 && tile_no == 3 && tid == 0) {
+                for (int pr = 0; pr < 12; ++pr) {
+                    printf("st %2d:", pr + 4);
+                    for (int e = 0; e < 13; ++e) printf(" %6lld", s_ev[pr][e] - s_ev[0][0]);
+                    printf("\n");
+                }
+            }
+            ++tile_no;
+#endif
             cur += np;
         }
     }

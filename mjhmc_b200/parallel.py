@@ -172,16 +172,26 @@ def allgather_samples(S, group=None):
     return torch.cat([p[:, :, :n] for p, n in zip(parts, sizes)], dim=2)
 
 
-def autocorr_partial(S, n_lags=None, circular=True):
+def autocorr_partial(S, n_lags=None, circular=True, method="auto"):
     """Un-normalised autocorrelation sums of the LOCAL particles on the GPU (K7):
     ac[tau] = sum_{k,i,t} x[k,t,i] x[k,(t+tau) mod T,i]  (circular; linear: only t + tau < T);
-    S is the device tensor (ndims, T, n_local)."""
+    S is the device tensor (ndims, T, n_local).  method: "fft" (the reference's route, autocor.py:37-49: T a power of
+    two up to 4096), "direct" (products, any T and the linear window) or "auto" (fft where it applies)."""
     lib = _lib.load()
     d, T, n = S.shape
     n_lags = T if n_lags is None else int(n_lags)
     ac = torch.zeros(n_lags, dtype=torch.float64, device=S.device)
-    _lib.check(lib.mjhmc_autocorr(_device.dtype_code(S.dtype), d, _device.ptr(S), S.stride(0), S.stride(1), n, T,
-                                  n_lags, 1 if circular else 0, _device.ptr(ac), _device.stream_ptr(S.device)), "autocorr")
+    code, stream = _device.dtype_code(S.dtype), _device.stream_ptr(S.device)
+    fft_bytes = int(lib.mjhmc_autocorr_fft_scratch_bytes(T)) if (circular and n_lags <= T) else -1
+    if method == "fft" and fft_bytes < 0:
+        raise ValueError("method='fft' needs the circular sums of a power-of-two T in [16, 4096]")
+    if method != "direct" and fft_bytes >= 0:
+        scratch = torch.empty(fft_bytes, dtype=torch.uint8, device=S.device)
+        _lib.check(lib.mjhmc_autocorr_fft(code, d, _device.ptr(S), S.stride(0), S.stride(1), n, T, n_lags, _device.ptr(ac),
+                                          _device.ptr(scratch), stream), "autocorr_fft")
+        return ac
+    _lib.check(lib.mjhmc_autocorr(code, d, _device.ptr(S), S.stride(0), S.stride(1), n, T, n_lags, 1 if circular else 0,
+                                  _device.ptr(ac), stream), "autocorr")
     return ac
 
 

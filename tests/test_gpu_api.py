@@ -204,6 +204,33 @@ def test_autocorrelation_kernels_multi_pass_and_ragged(T, n_lags, N):
     np.testing.assert_allclose(c32, want_c[:min(n_lags, 16)], rtol=1e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize("T,n_lags,N,d", [(16, 16, 1, 1), (32, 20, 7, 2), (128, 128, 33, 3), (1024, 1024, 50, 2),
+                                         (2048, 100, 19, 1), (4096, 4096, 6, 1)])
+def test_fft_autocorrelation_kernel(T, n_lags, N, d):
+    """K7b (csrc/autocorr_fft.cu): the route the reference takes (misc/autocor.py:37-49 -- FFT along time, |.|^2, inverse
+    FFT) against the literal circular products and against the direct-product kernel: radix-2 + radix-4 stage mixes
+    (log2 T odd and even), odd particle counts (an unpaired real series), tiles that do not fill, fewer lags than steps,
+    float32 samples."""
+    import torch
+    from mjhmc_b200 import parallel
+    rs = np.random.RandomState(T + N)
+    x = np.cumsum(rs.randn(d, T, N), axis=1) * 0.1 + rs.randn(d, T, N) + 0.3       # (d, T, N) device layout, non-zero mean
+    S = torch.as_tensor(x, device="cuda")
+    fft = parallel.autocorr_partial(S, n_lags=n_lags, method="fft").cpu().numpy()
+    want = np.real(np.fft.ifft(np.abs(np.fft.fft(x, axis=1)) ** 2, axis=1)).sum(axis=(0, 2))[:n_lags]
+    np.testing.assert_allclose(fft, want, rtol=1e-11, atol=1e-9 * want[0])
+    direct = parallel.autocorr_partial(S, n_lags=min(n_lags, 64), method="direct").cpu().numpy()
+    np.testing.assert_allclose(fft[:len(direct)], direct, rtol=1e-11, atol=1e-9 * want[0])
+    f32 = parallel.autocorr_partial(S.float(), n_lags=n_lags, method="fft").cpu().numpy()
+    np.testing.assert_allclose(f32, want, rtol=1e-5, atol=1e-5 * want[0])
+    # normalised curve == the oracle's fft_autocor on the reference layout (d, N, T)
+    if n_lags == T:
+        ref = orc.fft_autocor(np.ascontiguousarray(x.transpose(0, 2, 1)))
+        np.testing.assert_allclose(fft / fft[0], ref, atol=1e-10)
+    with pytest.raises(ValueError):
+        parallel.autocorr_partial(torch.as_tensor(x[:, :T - 1], device="cuda"), method="fft")
+
+
 @pytest.mark.parametrize("kind", ["ControlHMC", "MarkovJumpHMC"])
 def test_shard_invariance_single_gpu(kind):
     """T7 on one device: the cloud sampled whole == the two halves sampled separately with

@@ -28,6 +28,56 @@ __global__ void probe(int N, int n_mma, int n_acc, int mode, long long* out) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tm = s_tmem;
     const uint32_t ncores = 14;
+    __shared__ volatile int s_stop;
+    if (tid == 0) s_stop = 0;
+    __syncthreads();
+    if ((mode & 8) && warp == 0) {
+        // all lanes converged, one elected lane issues: descriptors stay in uniform registers (dense_tc.cu)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)N >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t a0 = smem_u32(base), b0 = smem_u32(base) + 3 * 14 * 2048;
+        const uint64_t a_hi = make_desc(0, 2048, 128), b_hi = make_desc(0, 128, ncores * 128);
+        uint32_t a_lo[3], b_lo[3];
+        for (int pl = 0; pl < 3; ++pl) { a_lo[pl] = ((a0 + pl * 14 * 2048) >> 4) & 0x3FFF; b_lo[pl] = ((b0 + pl * ncores * ncores * 128) >> 4) & 0x3FFF; }
+        const int ksteps = n_mma / 6;
+        for (int rep = 0; rep < 3; ++rep) {
+            const long long t0 = clock64();
+            for (int c = 0; c < (ksteps + 1) / 2; ++c) {
+                uint32_t el = 0;
+                asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(el));
+                if (el) {
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const int kg = 2 * c + kk;
+                        if (kg < ksteps) {
+                            const uint32_t ao = (uint32_t)kg * 256u, bo = (uint32_t)kg * 16u;
+                            const uint64_t a0d = a_hi | (uint64_t)(a_lo[0] + ao), a1d = a_hi | (uint64_t)(a_lo[1] + ao), a2d = a_hi | (uint64_t)(a_lo[2] + ao);
+                            const uint64_t b0d = b_hi | (uint64_t)(b_lo[0] + bo), b1d = b_hi | (uint64_t)(b_lo[1] + bo), b2d = b_hi | (uint64_t)(b_lo[2] + bo);
+#define MMA2(A, B, ACC) asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tm), "l"(A), "l"(B), "r"(idesc), "r"(ACC) : "memory")
+                            MMA2(a0d, b0d, kg > 0 ? 1u : 0u); MMA2(a0d, b1d, 1u); MMA2(a1d, b0d, 1u); MMA2(a1d, b1d, 1u); MMA2(a0d, b2d, 1u); MMA2(a2d, b0d, 1u);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            if (tid == 0) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+            const long long t1 = clock64();
+            asm volatile("{\n.reg .pred p;\nW2:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D2;\nbra W2;\nD2:\n}\n" ::"r"(smem_u32(&bar)), "r"((uint32_t)(rep & 1)) : "memory");
+            const long long t2 = clock64();
+            if (tid == 0) { out[rep * 2] = t1 - t0; out[rep * 2 + 1] = t2 - t0; }
+        }
+        if (tid == 0) s_stop = 1;
+    } else if ((mode & 8) && warp > 0) {
+        // background traffic of "epilogue" warps while the MMAs run
+        uint8_t* scratch = base + 150000 + tid * 16;
+        uint32_t u[8];
+        while (!s_stop) {
+            if (mode & (16 | 64)) *reinterpret_cast<uint4*>(scratch) = make_uint4(tid, 1, 2, 3);
+            if (mode & 16) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (mode & 32) asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\ntcgen05.wait::ld.sync.aligned;"
+                                        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                                        : "r"(tm + ((uint32_t)((warp & 3) * 32) << 16) + 256u) : "memory");
+        }
+    } else
     if (tid == 0) {
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)N >> 3) << 17) | ((128u >> 4) << 24);
         const uint32_t a0 = smem_u32(base), b0 = smem_u32(base) + 3 * 14 * 2048;
@@ -80,7 +130,7 @@ int main(int argc, char** argv) {
     long long* out; cudaMalloc(&out, 64);
     const int smem = 180000;
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    probe<<<1, 128, smem>>>(N, n_mma, n_acc, mode, out);
+    probe<<<1, (mode & 128) ? 512 : 128, smem>>>(N, n_mma, n_acc, mode, out);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[6]; cudaMemcpy(h, out, sizeof h, cudaMemcpyDeviceToHost);
     printf("N=%d n_mma=%d n_acc=%d mode=%d: %s  issue %lld cyc, done %lld cyc -> %.1f cyc/MMA (nominal %d)\n", N, n_mma, n_acc, mode,
