@@ -784,11 +784,14 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads / strong-scaling leg")
+    ap.add_argument("--ess-block", type=int, default=None, help="particles per block of the ESS leg (developer knob)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="strong: the workload's particle count is the TOTAL, split over the ranks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     w = WORKLOADS[args.workload]
+    if args.ess_block and w.get("ess"):
+        w = dict(w, ess=dict(w["ess"], block=args.ess_block))
 
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:

@@ -219,8 +219,9 @@ def test_fft_autocorrelation_kernel(T, n_lags, N, d):
     fft = parallel.autocorr_partial(S, n_lags=n_lags, method="fft").cpu().numpy()
     want = np.real(np.fft.ifft(np.abs(np.fft.fft(x, axis=1)) ** 2, axis=1)).sum(axis=(0, 2))[:n_lags]
     np.testing.assert_allclose(fft, want, rtol=1e-11, atol=1e-9 * want[0])
-    direct = parallel.autocorr_partial(S, n_lags=min(n_lags, 64), method="direct").cpu().numpy()
-    np.testing.assert_allclose(fft[:len(direct)], direct, rtol=1e-11, atol=1e-9 * want[0])
+    if T <= 1024:                                   # (the direct kernel keeps a T x 16 tile in shared memory)
+        direct = parallel.autocorr_partial(S, n_lags=min(n_lags, 64), method="direct").cpu().numpy()
+        np.testing.assert_allclose(fft[:len(direct)], direct, rtol=1e-11, atol=1e-9 * want[0])
     f32 = parallel.autocorr_partial(S.float(), n_lags=n_lags, method="fft").cpu().numpy()
     np.testing.assert_allclose(f32, want, rtol=1e-5, atol=1e-5 * want[0])
     # normalised curve == the oracle's fft_autocor on the reference layout (d, N, T)

@@ -136,8 +136,8 @@ def _coupling_worker(rank, world_size, port, out, backend):
         attempts = s._attempt
         dwell = parallel.allgather_samples(torch.as_tensor(s.dwelling_times, device=device).reshape(1, 1, -1))
         # ---- resampling over the whole cloud
-        np.random.seed(3)
         s2 = _mj(X0, V0, lo, hi, device, True, True, dict(epsilon=0.7, beta=0.5, num_leapfrog_steps=2))
+        np.random.seed(3)                 # the sorted uniforms of the resampler are host draws (rank 0 draws, all ranks share)
         R = s2.sample(5)
         Rfull = parallel.allgather_resampled(R, s2.resample_columns, 5 * N)
         if rank == 0:
@@ -155,8 +155,8 @@ def _coupling_worker(rank, world_size, port, out, backend):
             assert o.attempt == n + 2
             np.testing.assert_allclose(S1.cpu().numpy().reshape(2, -1), Xo, rtol=1e-10, atol=1e-12)
             assert list(counters.values()) == [o.counters()[k] for k in ("l", "f", "fl", "r", "E", "dEdX")]
-            np.random.seed(3)
             s3 = _mj(X0, V0, 0, N, device, True, None, dict(epsilon=0.7, beta=0.5, num_leapfrog_steps=2))
+            np.random.seed(3)
             R1 = s3.sample(5)
             np.testing.assert_array_equal(Rfull, R1)
             out.put("ok")

@@ -32,8 +32,10 @@ def test_golden_trajectory_per_iteration_fp64(name):
         st = s.state
         assert helpers.rel_err(st.X, g["X"][it]) < TOL["float64"], (name, it)
         assert helpers.rel_err(st.V, g["V"][it]) < TOL["float64"], (name, it)
-        assert helpers.rel_err(st.EX[0], g["EX"][it]) < TOL["float64"]
-        assert helpers.rel_err(st.EV[0], g["EV"][it]) < TOL["float64"]
+        # energies are sums of O(1) terms that cancel (sum of cosines): their error follows the positions' error
+        # times |dE/dx|, not their own magnitude, so they are held to 1e-10 of the array's RMS
+        assert helpers.rel_err(st.EX[0], g["EX"][it], floor_frac=1.0) < TOL["float64"]
+        assert helpers.rel_err(st.EV[0], g["EV"][it], floor_frac=1.0) < TOL["float64"]
         assert _counters(s, dist) == list(g["counters"][it]), (name, it)
         if name.startswith(("MarkovJumpHMC", "ContinuousTimeHMC")):
             fin = np.isfinite(g["dwell"][it])
