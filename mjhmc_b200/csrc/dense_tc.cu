@@ -40,8 +40,9 @@ constexpr int kTcEpiThreads = kTcRows * kTcSplit;  // 16 warps; warp w reads TME
 constexpr int kTcThreads = kTcEpiThreads + 32;     // + the MMA-issuing warp
 constexpr int kTcMaxP = 112;                       // padded dims / experts (K and N of the MMAs), a multiple of 16
 constexpr int kTcCPT = 4;                          // 8-wide core columns per thread (and K chunks per product)
-constexpr int kTcCoreColBytes = 2048;              // one 8-wide core column of an A plane: 16 row groups x 128 B
-constexpr int kTcTmemCols = 256;                   // two accumulators of 128 columns
+constexpr int kTcTmemCols = 512;                   // two accumulators of 128 columns + three A planes of 64
+constexpr uint32_t kTcACol = 256;                  // first TMEM column of A plane 0
+constexpr uint32_t kTcPlaneCols = 64;              // TMEM columns per A plane (112 bf16 = 56 columns, padded)
 constexpr int kTcTabs = 5;                         // ProductOfT per-expert tables: nu+1, nu^2, b, (nu+1)/2, 1/nu^2
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -70,7 +71,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -81,14 +81,22 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] . B[smem]: the A operand (job rows x 16 bf16, two per 32-bit column, lane = row) is read from
+// tensor memory, only B comes from shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// 4 consecutive 32-bit columns (8 bf16) of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&u)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+                 ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // one lane of a converged warp (elect.sync): keeps the control flow warp-uniform, so the descriptor arithmetic of the
 // MMA warp stays in uniform registers instead of being moved there (R2UR) in front of every UTCHMMA
 __device__ __forceinline__ bool elect_one() {
@@ -127,25 +135,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes,
     return d;
 }
 
-// byte offset of the 16-byte row (8 bf16) of job row m in core column kc (columns 8kc .. 8kc+7) of an A plane:
-// K-major, 8-row x 16-byte core matrices, the 16 row groups of one core column contiguous (SBO = 128, LBO = 2048),
-// so the 32 lanes of a warp store 32 consecutive 16-byte rows -- conflict-free 128-bit stores.
-__device__ __forceinline__ uint32_t a_row_offset(int m, int kc) {
-    return (uint32_t)kc * kTcCoreColBytes + (uint32_t)(m >> 3) * 128u + (uint32_t)(m & 7) * 16u;
-}
-
 // Core column (8 dims) that thread slice q owns in K chunk c.  The first chunk is ONE K step (cores 0, 1: slices 0 and
 // 1 only), the others two (cores 4c-2 .. 4c+1): the MMA warp can start a product after half the usual wait, and
 // every core 0 .. 13 has exactly one owner.  kTcMaxP / 8 = "none" (fails every bound check).
 __device__ __forceinline__ int tc_core(int c, int q) { return c ? 4 * c - 2 + q : (q < 2 ? q : kTcMaxP / 8); }
 
-// x = x0 + x1 + x2 with bf16 parts (round to nearest; the remainders are exact): 8 values -> one 16-byte row per plane
-__device__ __forceinline__ void split3_store(const float (&x)[8], uint8_t* plane0, uint32_t plane_bytes, uint32_t off) {
+// x = x0 + x1 + x2 with bf16 parts (round to nearest; the remainders are exact): 8 values -> 4 packed columns per plane
+// of this thread's TMEM lane.  taddr = lane | first column of the core in plane 0; the planes are kTcPlaneCols apart.
+__device__ __forceinline__ void split3_store(const float (&x)[8], uint32_t taddr) {
     uint32_t p0[4], p1[4], p2[4];
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
         const float a = x[2 * jj], b = x[2 * jj + 1];
-        const __nv_bfloat162 h0 = __floats2bfloat162_rn(a, b);                 // .x = a: low half = lower address
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(a, b);                 // .x = a: low half = the even K element
         const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0);
         const float ra = a - __uint_as_float(u0 << 16), rb = b - __uint_as_float(u0 & 0xFFFF0000u);
         const __nv_bfloat162 h1 = __floats2bfloat162_rn(ra, rb);
@@ -154,9 +156,9 @@ __device__ __forceinline__ void split3_store(const float (&x)[8], uint8_t* plane
         const __nv_bfloat162 h2 = __floats2bfloat162_rn(sa, sb);
         p0[jj] = u0; p1[jj] = u1; p2[jj] = *reinterpret_cast<const uint32_t*>(&h2);
     }
-    *reinterpret_cast<uint4*>(plane0 + off) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
-    *reinterpret_cast<uint4*>(plane0 + plane_bytes + off) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
-    *reinterpret_cast<uint4*>(plane0 + 2u * plane_bytes + off) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+    tmem_st4(taddr, p0);
+    tmem_st4(taddr + kTcPlaneCols, p1);
+    tmem_st4(taddr + 2u * kTcPlaneCols, p2);
 }
 
 // Pre-tile the matrix (fp32, rows x cols row-major) into three bf16 planes of 8-row x 16-byte core matrices:
@@ -212,11 +214,9 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     const int ncores = P >> 3;
     const int ksteps = P >> 4;
     const int nchunks = (ksteps + 2) >> 1;         // K chunks of a product: steps [0,1), [1,3), [3,5), [5,7)
-    const uint32_t a_plane = (uint32_t)ncores * kTcCoreColBytes;
     const uint32_t b_plane = (uint32_t)ncores * ncores * 128u;
     const uint32_t ws_bytes = 3u * b_plane + (POT ? (uint32_t)(kTcTabs * P * 4) : 0u);
-    uint8_t* A0 = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);
-    uint8_t* B0 = A0 + 3u * a_plane;
+    uint8_t* B0 = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);
     const float* tab = reinterpret_cast<const float*>(B0 + 3u * b_plane);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool epi = tid < kTcEpiThreads;
@@ -246,16 +246,15 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     // N = P, M = 128; bit 16 selects the MN-major view of B
     const uint32_t idesc_k = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t idesc_mn = idesc_k | (1u << 16);
-    const uint32_t a_addr = smem_u32(A0), b_addr = smem_u32(B0);
+    const uint32_t b_addr = smem_u32(B0);
     // descriptor pieces for the MMA warp: the 14-bit start address (16-byte units) of every plane is the low word,
     // LBO / SBO / version the high part; a K step advances the start address by a constant
-    const uint64_t a_desc_hi = make_desc(0, kTcCoreColBytes, 128);
     const uint64_t b_desc_hi_k = make_desc(0, 128, (uint32_t)ncores * 128u);            // K-major view: N = row, K = column
     const uint64_t b_desc_hi_mn = make_desc(0, (uint32_t)ncores * 128u, 128);           // MN-major view: N = column, K = row
     const uint32_t b_kstep_mn = (uint32_t)(2 * ncores * 128) >> 4;
-    uint32_t a_lo[3], b_lo[3];
+    uint32_t b_lo[3];
 #pragma unroll
-    for (int pl = 0; pl < 3; ++pl) { a_lo[pl] = ((a_addr + pl * a_plane) >> 4) & 0x3FFFu; b_lo[pl] = ((b_addr + pl * b_plane) >> 4) & 0x3FFFu; }
+    for (int pl = 0; pl < 3; ++pl) b_lo[pl] = ((b_addr + pl * b_plane) >> 4) & 0x3FFFu;
 
     float eps = (float)p.eps, nhe = (float)(-p.eps / 2.0), neg_eps = nhe + nhe;
     // pinned: ptxas otherwise re-derives these from the double in the constant bank inside the sweep (DMUL + F2F per use)
@@ -267,6 +266,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     uint32_t pc = 0;                               // running product counter: barrier parities, accumulator choice
     // my TMEM window: lane quarter of my warp (warp % 4), accumulator column of core column kc = 8 kc
     const uint32_t my_lane = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t a_lane = tmem_base + my_lane + kTcACol;       // my row of A plane 0 (core kc = columns 4 kc ..)
 
     // contiguous particle range of this CTA
     const long long r0 = p.n * (long long)blockIdx.x / gridDim.x, r1 = p.n * (long long)(blockIdx.x + 1) / gridDim.x;
@@ -364,8 +364,8 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                 for (int c = 0; c < kTcCPT; ++c) {
                     if (c < nchunks) {
                         const int kc = tc_core(c, q);
-                        if (kc < ncores) split3_store(x[c], A0, a_plane, a_row_offset(m, kc));
-                        fence_async_smem();
+                        if (kc < ncores) split3_store(x[c], a_lane + (uint32_t)(kc * 4));
+                        tmem_st_wait();
                         tc_fence_before();
                         mbar_arrive(&bar_chunk[c]);
                     }
@@ -406,9 +406,9 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                                         const float yy = y[j] + bb[j];
                                         g[j] = __fdividef(a1[j] * yy, n2[j] + yy * yy);
                                     }
-                                    split3_store(g, A0, a_plane, a_row_offset(m, kc));
+                                    split3_store(g, a_lane + (uint32_t)(kc * 4));
                                 }
-                                fence_async_smem();
+                                tmem_st_wait();
                                 tc_fence_before();
                                 mbar_arrive(&bar_chunk[c]);
                                 TCX_EV(2 * st, 1 + c)
@@ -444,12 +444,10 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                                         x[c][j] = fmaf(eps, v[c][j], x[c][j]);
                                     }
 #ifndef TCX_NOSTORE
-                                    split3_store(x[c], A0, a_plane, a_row_offset(m, kc));
+                                    split3_store(x[c], a_lane + (uint32_t)(kc * 4));
 #endif
                                 }
-#ifndef TCX_NOFENCE
-                                fence_async_smem();
-#endif
+                                tmem_st_wait();
                                 tc_fence_before();
                                 mbar_arrive(&bar_chunk[c]);
                                 TCX_EV(POT ? 2 * st + 1 : st, 1 + c)
@@ -478,11 +476,11 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                                     if (st < L) {
 #pragma unroll
                                         for (int j = 0; j < 8; ++j) x[c][j] = fmaf(eps, v[c][j], x[c][j]);
-                                        split3_store(x[c], A0, a_plane, a_row_offset(m, kc));
+                                        split3_store(x[c], a_lane + (uint32_t)(kc * 4));
                                     }
                                 }
                                 if (st < L) {
-                                    fence_async_smem();
+                                    tmem_st_wait();
                                     tc_fence_before();
                                     mbar_arrive(&bar_chunk[c]);
                                 }
@@ -522,18 +520,17 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                             for (int kk = 0; kk < 2; ++kk) {
                                 const int kg = 2 * c - 1 + kk;
                                 if (kg >= 0 && kg < ksteps) {
-                                    const uint32_t ao = (uint32_t)kg * 256u, bo = (uint32_t)kg * bstep;
-                                    const uint64_t a0d = a_desc_hi | (uint64_t)(a_lo[0] + ao), a1d = a_desc_hi | (uint64_t)(a_lo[1] + ao),
-                                                   a2d = a_desc_hi | (uint64_t)(a_lo[2] + ao);
+                                    const uint32_t bo = (uint32_t)kg * bstep;
+                                    const uint32_t a0t = tmem_base + kTcACol + (uint32_t)kg * 8u, a1t = a0t + kTcPlaneCols, a2t = a1t + kTcPlaneCols;
                                     const uint64_t b0d = bhi | (uint64_t)(b_lo[0] + bo), b1d = bhi | (uint64_t)(b_lo[1] + bo),
                                                    b2d = bhi | (uint64_t)(b_lo[2] + bo);
 #ifndef TCX_NOMMA
-                                    umma_bf16(dacc, a0d, b0d, idesc, kg > 0 ? 1u : 0u);
-                                    umma_bf16(dacc, a0d, b1d, idesc, 1u);
-                                    umma_bf16(dacc, a1d, b0d, idesc, 1u);
-                                    umma_bf16(dacc, a1d, b1d, idesc, 1u);
-                                    umma_bf16(dacc, a0d, b2d, idesc, 1u);
-                                    umma_bf16(dacc, a2d, b0d, idesc, 1u);
+                                    umma_bf16_ts(dacc, a0t, b0d, idesc, kg > 0 ? 1u : 0u);
+                                    umma_bf16_ts(dacc, a0t, b1d, idesc, 1u);
+                                    umma_bf16_ts(dacc, a1t, b0d, idesc, 1u);
+                                    umma_bf16_ts(dacc, a1t, b1d, idesc, 1u);
+                                    umma_bf16_ts(dacc, a0t, b2d, idesc, 1u);
+                                    umma_bf16_ts(dacc, a2t, b0d, idesc, 1u);
 #endif
                                 }
                             }
@@ -734,7 +731,7 @@ template <bool POT>
 static cudaError_t launch_tc_T(const LaunchParams& p, cudaStream_t stream) {
     int P, nc;
     tc_shape(p.d, P, nc);
-    const size_t smem = 3 * (size_t)nc * kTcCoreColBytes + 3 * (size_t)nc * nc * 128 + (POT ? kTcTabs * P * 4 : 0) + 1024;
+    const size_t smem = 3 * (size_t)nc * nc * 128 + (POT ? kTcTabs * P * 4 : 0) + 1024;
     static int sms = 0;
     if (!sms) {
         int dev = 0;
