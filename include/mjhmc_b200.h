@@ -128,6 +128,9 @@ typedef struct mjhmc_outputs {
     uint8_t *choice;            /* (n_iter, n): operator taken; MJ 0=L 1=F 2=R, CT 0=F 1=FL 2=R,
                                    discrete bit0=accepted bit1=flipped bit2=R fired */
     int64_t *counters;          /* [MJHMC_COUNTER_ROWS][MJHMC_N_COUNTERS], +=; reset before every launch */
+    double  *energy;            /* (n_iter, n): H() of the state after every iteration (hmc_state.py:80-84), what
+                                   experiments/spectral.py:33-45,186-208 reads with sampler.state.H() after each
+                                   sampling_iteration().  Register-resident and unfused kernels only (NULL elsewhere) */
 } mjhmc_outputs;
 
 const char *mjhmc_last_error(void);
@@ -244,6 +247,15 @@ int mjhmc_autocorr(int32_t dtype, int32_t ndims, const void *samples, int64_t st
 int64_t mjhmc_autocorr_fft_scratch_bytes(int32_t T);
 int mjhmc_autocorr_fft(int32_t dtype, int32_t ndims, const void *samples, int64_t stride_k, int64_t stride_it, int64_t n,
                        int32_t T, int32_t n_lags, double *ac, void *scratch, void *stream);
+
+/* Replaces the counter-polling loop of experiments/spectral.py:107-131 (ladder_heatmap): every particle walks its
+ * state ladder (samplers/algebraic_hmc.py:485-519: L moves k2 by +1 / -1 depending on the flip bit k1, F toggles k1,
+ * R starts a new ladder at [0, 0]) through the operator choices a MarkovJumpHMC launch recorded (0 = L, 1 = F, 2 = R)
+ * and counts the visits of node (k1, k2):  visits[k1 * (2 K + 1) + k2 + K] += 1 for |k2| <= K, visits[2 (2 K + 1)] counts
+ * the steps outside the window.  state: (n, 2) int32 ladder position carried between calls (zeros to start).
+ * choice: (n_iter, n) uint8.  visits: int64[2 (2 K + 1) + 1]. */
+int mjhmc_ladder_visits(const uint8_t *choice, int64_t n_iter, int64_t n, int32_t K, int32_t *state, int64_t *visits,
+                        void *stream);
 
 /* Replaces the Welford loop of online_variance (misc/gen_mj_init.py:76-98) for one chunk of samples:
  * out[0] += sum x, out[1] += sum x^2 over `count` contiguous elements (double accumulation). */

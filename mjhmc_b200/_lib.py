@@ -52,7 +52,7 @@ class FullState(C.Structure):
 class Outputs(C.Structure):
     _fields_ = [("samples", C.c_void_p), ("stride_k", C.c_int64), ("stride_it", C.c_int64),
                 ("dwell", C.c_void_p), ("dwell_last", C.c_void_p), ("choice", C.c_void_p),
-                ("counters", C.c_void_p)]
+                ("counters", C.c_void_p), ("energy", C.c_void_p)]
 
 
 # every symbol include/mjhmc_b200.h declares: name -> (restype, argtypes)
@@ -90,6 +90,7 @@ SYMBOLS = {
     "mjhmc_autocorr_fft_scratch_bytes": (C.c_int64, [C.c_int32]),
     "mjhmc_autocorr_fft": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                      C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mjhmc_ladder_visits": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mjhmc_moments": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
 }
 

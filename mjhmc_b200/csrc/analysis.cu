@@ -294,6 +294,42 @@ cudaError_t launch_autocorr(int dtype, int d, const void* samples, long long str
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ state-ladder walk
+// experiments/spectral.py:107-131: one thread per particle replays its recorded operator choices on the dihedral state
+// group of samplers/algebraic_hmc.py:485-519 and counts node visits in a (2, 2K+1) window kept in shared memory.
+__global__ void __launch_bounds__(256) ladder_visits_kernel(const unsigned char* __restrict__ choice, long long n_iter,
+                                                            long long n, int K, int* __restrict__ state,
+                                                            unsigned long long* __restrict__ visits) {
+    extern __shared__ unsigned int lv[];             // 2 (2K + 1) + 1 block-local counts
+    const int W = 2 * K + 1, nb = 2 * W + 1;
+    for (int j = threadIdx.x; j < nb; j += blockDim.x) lv[j] = 0u;
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        int k1 = state[2 * i], k2 = state[2 * i + 1];
+        for (long long it = 0; it < n_iter; ++it) {
+            const unsigned c = choice[it * n + i];
+            if (c == 2u) { k1 = 0; k2 = 0; }                          // R: a new ladder
+            else if (c == 0u) k2 += k1 ? -1 : 1;                      // L = F (F L): moves along the ladder, keeps k1
+            else if (c == 1u) k1 ^= 1;                                // F (any other code: no move on the ladder)
+            const int slot = (k2 >= -K && k2 <= K) ? k1 * W + k2 + K : 2 * W;
+            atomicAdd(&lv[slot], 1u);
+        }
+        state[2 * i] = k1; state[2 * i + 1] = k2;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < nb; j += blockDim.x) if (lv[j]) atomicAdd(visits + j, (unsigned long long)lv[j]);
+}
+
+cudaError_t launch_ladder_visits(const unsigned char* choice, long long n_iter, long long n, int K, int* state,
+                                 long long* visits, cudaStream_t s) {
+    if (n == 0 || n_iter == 0) return cudaSuccess;
+    const size_t smem = sizeof(unsigned int) * (2 * (2 * (size_t)K + 1) + 1);
+    if (smem > 48 * 1024) return cudaErrorInvalidValue;
+    ladder_visits_kernel<<<(unsigned)((n + 255) / 256), 256, smem, s>>>(choice, n_iter, n, K, state, (unsigned long long*)visits);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ moments
 // out[0] += sum x, out[1] += sum x^2 over `count` contiguous elements (online_variance of
 // misc/gen_mj_init.py:76-98 in chunks: the caller merges the chunks with Chan's formula).

@@ -12,5 +12,7 @@ bool autocorr_fft_supported(int Tn, int circular);
 long long autocorr_fft_scratch_bytes(int Tn);
 cudaError_t launch_autocorr_fft(int dtype, int d, const void* samples, long long stride_k, long long stride_it,
                                 long long n, int Tn, int n_lags, double* ac, double* scratch, cudaStream_t s);
+cudaError_t launch_ladder_visits(const unsigned char* choice, long long n_iter, long long n, int K, int* state,
+                                 long long* visits, cudaStream_t s);
 cudaError_t launch_moments(int dtype, const void* x, long long count, double* out, cudaStream_t s);
 }

@@ -83,7 +83,7 @@ static int fill_rng(LaunchParams& p, const mjhmc_rng* rng) {
 
 static void fill_outputs(LaunchParams& p, const mjhmc_outputs* o) {
     p.samples = o->samples; p.s_stride_k = o->stride_k; p.s_stride_it = o->stride_it;
-    p.dwell = o->dwell; p.dwell_last = o->dwell_last; p.choice = o->choice;
+    p.dwell = o->dwell; p.dwell_last = o->dwell_last; p.choice = o->choice; p.energy = o->energy;
     p.counters = (unsigned long long*)o->counters;
 }
 
@@ -173,6 +173,8 @@ static int sample_impl(const mjhmc_dist* dist, const mjhmc_hp* hp, const mjhmc_r
     p.Hc_in = in->H_cache; p.Hc_out = out->H_cache; p.ca_in = in->cache_active; p.ca_out = out->cache_active;
     p.n = in->n; p.ld = in->ld; p.n_iter = n_iter;
     if (p.n == 0) return 0;
+    if (o->energy && (force_stream || !is_elementwise(dist->kind) || !fused_template_dim(dist->ndims)))
+        return fail("outputs.energy is written by the register-resident and unfused kernels only");
     if (force_stream) {
         if (!stream_supported(dist->dtype, dist->kind, dist->ndims))
             return fail("no streaming kernel for this distribution / ndims (separable energies, ndims <= 128)");
@@ -335,6 +337,13 @@ int mjhmc_autocorr_fft(int32_t dtype, int32_t ndims, const void* samples, int64_
     if (n && n_lags && (!samples || !ac || !scratch)) return fail("NULL argument");
     return check(launch_autocorr_fft(dtype, ndims, samples, stride_k, stride_it, n, T, n_lags, ac, (double*)scratch,
                                      (cudaStream_t)stream), "autocorr_fft");
+}
+
+int mjhmc_ladder_visits(const uint8_t* choice, int64_t n_iter, int64_t n, int32_t K, int32_t* state, int64_t* visits,
+                        void* stream) {
+    if (n_iter < 0 || n < 0 || K < 0) return fail("bad sizes");
+    if (n_iter && n && (!choice || !state || !visits)) return fail("NULL argument");
+    return check(launch_ladder_visits(choice, n_iter, n, K, state, (long long*)visits, (cudaStream_t)stream), "ladder_visits");
 }
 
 int mjhmc_moments(int32_t dtype, const void* x, int64_t count, double* out, void* stream) {

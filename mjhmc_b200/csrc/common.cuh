@@ -27,7 +27,7 @@ struct LaunchParams {
     long long n, ld;
     // outputs
     void* samples; long long s_stride_k, s_stride_it;
-    double* dwell; double* dwell_last; uint8_t* choice;
+    double* dwell; double* dwell_last; uint8_t* choice; double* energy;
     unsigned long long* counters;
     // hyper-parameters
     int sampler, L, n_iter, d;

@@ -247,6 +247,7 @@ fused_sample_kernel(const __grid_constant__ LaunchParams p) {
                 }
                 if (p.dwell) p.dwell[(long long)it * p.n + i] = dwell;
                 if (p.choice) p.choice[(long long)it * p.n + i] = (uint8_t)choice;
+                if (p.energy) p.energy[(long long)it * p.n + i] = (double)(EX + EV);      // state.H() after the iteration
             }
         }
     }

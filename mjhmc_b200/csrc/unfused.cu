@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(kThreads) transition_kernel(const __grid_const
             if (p.dwell) p.dwell[i] = dwell;
             if (p.dwell_last && p.sampler != MJHMC_SAMPLER_DISCRETE) p.dwell_last[i] = dwell;
             if (p.choice) p.choice[i] = (uint8_t)choice;
+            if (p.energy) p.energy[i] = (double)(EX[i] + EV[i]);
         }
     }
     const unsigned int loc[6] = {n_l, n_f, n_fl, n_r, 0u, 0u};

@@ -11,3 +11,10 @@ def overrides(interface_class):
         assert method.__name__ in dir(interface_class)
         return method
     return overrider
+
+
+def package_path():
+    """Directory that holds the package and its data folders (``initializations/``, ``distr_data/``); the reference
+    searches sys.path for an entry containing 'MJHMC' (misc/utils.py:60-72)."""
+    import os
+    return os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -58,10 +58,67 @@ class HMCState(object):
     def get_state(self):
         return np.concatenate((self.X, self.V))
 
+    # -- the operators of hmc_state.py:86-129 on the host view.  Arithmetic stays on the GPU: the leapfrog pieces are
+    # the unfused kernels (mjhmc_kick_drift / mjhmc_kick), the gradient and energy the distribution's device
+    # evaluation, counted like the reference counts them (parent.dEdX / parent.E).
+    def _device_L(self, sign):
+        import torch
+        from .. import _device, _lib
+        par = self.parent
+        eng = par._engine
+        lib = _lib.load()
+        with eng.ctx():
+            X = _device.to_device(self.X, eng.dtype, eng.device)
+            V = _device.to_device(sign * self.V, eng.dtype, eng.device)
+            G = eng._callback(X, True, count=False)          # dEdX of the current state: evaluated when it was made
+            m, eps = X.shape[1], float(par.epsilon)
+            for _ in range(int(par.num_leapfrog_steps)):
+                _lib.check(lib.mjhmc_kick_drift(eng.code, eng.d, _device.ptr(X), _device.ptr(V), _device.ptr(G), m, m, eps,
+                                                eng._stream()), "kick_drift")
+                G = eng._callback(X, True)                    # counted: hmc_state.py:90 -> parent.dEdX
+                _lib.check(lib.mjhmc_kick(eng.code, eng.d, _device.ptr(V), _device.ptr(G), m, m, eps, eng._stream()), "kick")
+            eng._callback(X, False)                           # update_EX (hmc_state.py:99): one counted energy evaluation
+            self.X = X.double().cpu().numpy()
+            self.V = sign * V.double().cpu().numpy()
+        return self
+
+    def leapfrog(self):
+        """One leapfrog step (hmc_state.py:86-91)."""
+        par, keep = self.parent, self.parent.num_leapfrog_steps
+        par.num_leapfrog_steps = 1
+        try:
+            return self._device_L(1.0)
+        finally:
+            par.num_leapfrog_steps = keep
+
+    def L(self):
+        """Integration operator: num_leapfrog_steps leapfrog steps, then the energies (hmc_state.py:93-100)."""
+        return self._device_L(1.0)
+
     def F(self):
         """Explicit flip operator (hmc_state.py:102-107)."""
         self.V = -self.V
         return self
+
+    def FLF(self):
+        """F L F (hmc_state.py:109-119); the host view integrates every column (its cache flags describe the
+        sampler's device state, not this copy)."""
+        return self._device_L(-1.0)
+
+    def R(self):
+        """Momentum corruption V = V sqrt(1 - beta) + randn sqrt(beta) with the parent's beta (hmc_state.py:121-129)."""
+        beta = float(self.parent.beta)
+        self.V = self.V * np.sqrt(1 - beta) + np.random.randn(*self.V.shape) * np.sqrt(beta)
+        return self
+
+    def update(self, idx, state):
+        """Replace the columns idx of this state by those of `state` (hmc_state.py:63-72)."""
+        if len(idx) == 0:
+            return
+        self.X[:, idx] = state.X[:, idx]
+        self.V[:, idx] = state.V[:, idx]
+        self.cache_active[idx] = state.cache_active[idx]
+        self.H_cache[idx] = state.H_cache[idx]
 
     def reset_flf_cache(self):
         self.cache_active = np.zeros_like(self.cache_active)

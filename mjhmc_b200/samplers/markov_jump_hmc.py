@@ -181,7 +181,7 @@ class _Engine(object):
         st.ld = self.n
         return st
 
-    def _outputs(self, samples, it0, dwell, choice):
+    def _outputs(self, samples, it0, dwell, choice, energy=None):
         o = _lib.Outputs()
         esz = None
         if samples is not None:
@@ -193,6 +193,8 @@ class _Engine(object):
             o.dwell = dwell.data_ptr() + it0 * self.n * 8
         if choice is not None:
             o.choice = choice.data_ptr() + it0 * self.n
+        if energy is not None:
+            o.energy = energy.data_ptr() + it0 * self.n * 8
         o.dwell_last = self.dwell[self.cur ^ 1 if self.fused else self.cur].data_ptr()
         o.counters = self.counters.data_ptr()
         return o
@@ -225,7 +227,7 @@ class _Engine(object):
         self._launch_key = key
 
     # ---------------------------------------------------------------- fused launch
-    def launch(self, attempt0, n_iter, samples=None, it0=0, dwell=None, choice=None):
+    def launch(self, attempt0, n_iter, samples=None, it0=0, dwell=None, choice=None, energy=None):
         """Runs n_iter iterations from the current state into the spare buffers (no commit).
         Returns the folded counters of this launch."""
         with torch.cuda.device(self.device):
@@ -237,7 +239,7 @@ class _Engine(object):
                 if self.inj is not None and attempt0 + n_iter > self.inj["U"].shape[0]:
                     raise IndexError("injected draws exhausted")
                 src, dst = self._state(self.cur), self._state(self.cur ^ 1)
-                o = self._outputs(samples, it0, dwell, choice)
+                o = self._outputs(samples, it0, dwell, choice, energy)
                 entry = self.lib.mjhmc_sample_stream if self.kernel == "stream" else self.lib.mjhmc_sample_fused
                 if self.kernel_events is not None:      # bench.py: CUDA events right around the sampler kernel
                     ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -249,7 +251,7 @@ class _Engine(object):
                     self.kernel_events.append(ev)
                 self.launches += 1
                 return self._read_counters()
-            return self._launch_unfused(attempt0, n_iter, samples, it0, dwell, choice)
+            return self._launch_unfused(attempt0, n_iter, samples, it0, dwell, choice, energy)
 
     def commit(self):
         if self.fused:
@@ -294,7 +296,7 @@ class _Engine(object):
         EX = self._callback(X, False).reshape(-1)
         return G, EX, EV
 
-    def _launch_unfused(self, attempt0, n_iter, samples, it0, dwell, choice):
+    def _launch_unfused(self, attempt0, n_iter, samples, it0, dwell, choice, energy=None):
         s = self.sampler
         total = [0] * _lib.N_COUNTERS
         total[_lib.CNT_FAIL] = _lib.INT64_MAX
@@ -317,7 +319,7 @@ class _Engine(object):
             cur = _lib.FullState(X.data_ptr(), V.data_ptr(), self.G.data_ptr(), self.EX.data_ptr(), self.EV.data_ptr())
             prop = _lib.FullState(Xp.data_ptr(), Vp.data_ptr(), Gp.data_ptr(), EXp.data_ptr(), EVp.data_ptr())
             hp, rng = self._hp(), self._rng(attempt0 + it)
-            o = self._outputs(samples, it0 + it, dwell, choice)
+            o = self._outputs(samples, it0 + it, dwell, choice, energy)
             self.counters.copy_(self.cnt_template)
             _lib.check(self.lib.mjhmc_transition(self.code, self.d, C.byref(hp), C.byref(rng), self.n, self.n,
                                                  C.byref(cur), C.byref(prop), _device.ptr(H_flf),
@@ -491,13 +493,13 @@ class HMCBase(object):
             self.distribution.dEdX_count += cnt[_lib.CNT_DEDX]
             self.grad_evals_executed += cnt[_lib.CNT_EXEC]
 
-    def _run(self, n, samples=None, it0=0, dwell=None, choice=None):
+    def _run(self, n, samples=None, it0=0, dwell=None, choice=None, energy=None):
         """n sampling iterations, incl. the infinite-rate protocol (markov_jump_hmc.py:364-389)."""
         eng = self._engine
         done = 0
         while done < n:
             m = n - done
-            cnt = eng.launch(self._attempt, m, samples, it0 + done, dwell, choice)
+            cnt = eng.launch(self._attempt, m, samples, it0 + done, dwell, choice, energy)
             fail = cnt[_lib.CNT_FAIL]
             if self._group is not None:
                 # the back-off is batch-wide in the reference (markov_jump_hmc.py:376-389): every rank replays,
@@ -514,7 +516,7 @@ class HMCBase(object):
             if eng.fused:
                 if fail > 0:
                     # replay the iterations before the failing one (deterministic streams), keep them
-                    cnt = eng.launch(self._attempt, fail, samples, it0 + done, dwell, choice)
+                    cnt = eng.launch(self._attempt, fail, samples, it0 + done, dwell, choice, energy)
                     assert cnt[_lib.CNT_FAIL] == _lib.INT64_MAX
                     eng.commit()
                     self._accumulate(cnt)
@@ -527,13 +529,13 @@ class HMCBase(object):
             self._attempt += fail
             done += fail
             self._attempt += 1
-            self._on_infinite_rate(samples, it0 + done, dwell, choice)
+            self._on_infinite_rate(samples, it0 + done, dwell, choice, energy)
             done += 1
 
-    def _on_infinite_rate(self, samples, it, dwell, choice):
+    def _on_infinite_rate(self, samples, it, dwell, choice, energy=None):
         raise ValueError(INFINITE_RATE_MSG)
 
-    def _advance(self, n, record=True, want_dwell=False, want_choice=False):
+    def _advance(self, n, record=True, want_dwell=False, want_choice=False, want_energy=False):
         eng = self._engine
         self._sync_state_to_device()
         samples = dwell = choice = None
@@ -544,7 +546,10 @@ class HMCBase(object):
                 dwell = torch.empty((n, self.nbatch), dtype=torch.float64, device=eng.device)
             if want_choice:
                 choice = torch.empty((n, self.nbatch), dtype=torch.uint8, device=eng.device)
-            self._run(n, samples, 0, dwell, choice)
+            energy = torch.empty((n, self.nbatch), dtype=torch.float64, device=eng.device) if want_energy else None
+            self._run(n, samples, 0, dwell, choice, energy)
+        if want_energy:
+            return samples, dwell, choice, energy
         return samples, dwell, choice
 
     def _snapshot(self):
@@ -788,7 +793,7 @@ class MarkovJumpHMC(ContinuousTimeHMC):
     _sampler_code = _lib.SAMPLER_MARKOV_JUMP
 
     @overrides(ContinuousTimeHMC)
-    def _on_infinite_rate(self, samples, it, dwell, choice):
+    def _on_infinite_rate(self, samples, it, dwell, choice, energy=None):
         # infinite rate due to taking too large of a step (markov_jump_hmc.py:376-389):
         # take smaller steps, but go the same overall distance -- for the whole batch
         self.epsilon *= 0.5
@@ -796,7 +801,7 @@ class MarkovJumpHMC(ContinuousTimeHMC):
         depth = np.log(self.original_epsilon / self.epsilon) / np.log(2)
         print("Ecountered infinite rate, doubling back. Depth: {}".format(depth))
         self._engine.reset_cache()
-        self._run(1, samples, it, dwell, choice)
+        self._run(1, samples, it, dwell, choice, energy)
         # restore the old guys
         self.epsilon *= 2
         self.num_leapfrog_steps = int(self.num_leapfrog_steps / 2)

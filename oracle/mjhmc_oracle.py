@@ -185,6 +185,41 @@ class FunnelEnergy(Energy):
         return g
 
 
+class SparseImageCodeEnergy(Energy):
+    """misc/tf_distributions.py:204-284 (SparseImageCode) restated in numpy.
+
+    E = mean_p 1/2 ||patch_p - basis a_p||^2 + lmbda sum log(1 + x^2)   (:258-268; Laplace prior: sum |x|)
+    literal=True keeps the reference's row-major reshape of the (ndims, nbatch) state to (n_patches, nbatch,
+    n_coeffs) (:246); literal=False gives particle b the coefficient vectors a_p = x[p n_coeffs:(p+1) n_coeffs, b].
+    The gradient is the hand-derived autodiff of the graph (pinned against torch.autograd in tests/test_autograd_pin.py).
+    PARITY: TensorFlow is absent, the reference cannot run; pinned by autograd of the graph written op by op."""
+
+    def __init__(self, basis, patches, lmbda=0.01, cauchy=True, literal=False):
+        self.basis = np.asarray(basis, dtype=np.float64)          # [img_size, n_coeffs]
+        self.patches = np.asarray(patches, dtype=np.float64)      # [n_patches, img_size]
+        self.lmbda, self.cauchy, self.literal = lmbda, cauchy, literal
+        self.n_patches, self.n_coeffs = self.patches.shape[0], self.basis.shape[1]
+
+    def _shaped(self, X):
+        n = X.shape[1]
+        if self.literal:
+            return X.reshape(self.n_patches, n, self.n_coeffs)
+        return X.reshape(self.n_patches, self.n_coeffs, n).transpose(0, 2, 1)
+
+    def E(self, X):
+        resid = self.patches[:, None, :] - self._shaped(X) @ self.basis.T
+        rec = np.mean(np.sum(0.5 * resid ** 2, axis=-1), axis=0)
+        pen = np.sum(np.log(1 + X ** 2), axis=0) if self.cauchy else np.sum(np.abs(X), axis=0)
+        return (rec + self.lmbda * pen).reshape(1, -1)
+
+    def dEdX(self, X):
+        n = X.shape[1]
+        resid = self.patches[:, None, :] - self._shaped(X) @ self.basis.T
+        G = -(resid @ self.basis) / self.n_patches
+        G = G.reshape(X.shape[0], n) if self.literal else G.transpose(0, 2, 1).reshape(X.shape[0], n)
+        return G + self.lmbda * (2 * X / (1 + X ** 2) if self.cauchy else np.sign(X))
+
+
 class LambdaEnergy(Energy):
     """README.md:14-35 intent of LambdaDistribution (distributions.py:216-235)."""
     name = "Lambda"

@@ -79,3 +79,42 @@ def test_funnel_gradients_are_the_autodiff_of_the_reference_graph(scale, d):
     E_ref, G_ref = _autograd(lambda x: _funnel_neal_energy_torch(x, scale), X)
     np.testing.assert_allclose(np.asarray(neal.E(X)).reshape(-1), E_ref, rtol=1e-13, atol=1e-13)
     np.testing.assert_allclose(neal.dEdX(X), G_ref, rtol=1e-12, atol=1e-12)
+
+
+def _sparse_image_code_graph_torch(X, basis, patches, lmbda, cauchy, n_patches, n_coeffs):
+    """misc/tf_distributions.py:240-268 op by op (tf.reshape is row-major like torch.reshape)."""
+    n = X.shape[1]
+    patches_r = patches.reshape(n_patches, 1, -1)
+    shaped_state = X.reshape(n_patches, -1, n_coeffs, 1)
+    shaped_basis = basis.reshape(1, 1, basis.shape[0], n_coeffs).expand(n_patches, n, -1, -1)
+    reconstructions = torch.matmul(shaped_basis, shaped_state)[:, :, :, 0]
+    reconstruction_error = torch.sum(0.5 * (patches_r - reconstructions) ** 2, -1)
+    reconstruction_error = torch.mean(reconstruction_error, 0)
+    if cauchy:
+        sp_penalty = lmbda * torch.sum(torch.log(1 + X ** 2), 0)
+    else:
+        sp_penalty = lmbda * torch.sum(torch.abs(X), 0)
+    return reconstruction_error + sp_penalty
+
+
+@pytest.mark.parametrize("cauchy", [True, False])
+@pytest.mark.parametrize("n", [1, 4])
+def test_sparse_image_code_gradient_is_the_autodiff_of_the_reference_graph(cauchy, n):
+    rs = np.random.RandomState(11)
+    n_patches, n_coeffs, img = 3, 20, 12
+    basis, patches = rs.randn(img, n_coeffs) / 3, rs.randn(n_patches, img)
+    X = rs.randn(n_patches * n_coeffs, n)
+    lit = orc.SparseImageCodeEnergy(basis, patches, 0.01, cauchy, literal=True)
+    E_ref, G_ref = _autograd(lambda x: _sparse_image_code_graph_torch(x, torch.tensor(basis), torch.tensor(patches), 0.01,
+                                                                      cauchy, n_patches, n_coeffs), X)
+    np.testing.assert_allclose(np.asarray(lit.E(X)).reshape(-1), E_ref, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(lit.dEdX(X), G_ref, rtol=1e-12, atol=1e-13)
+    # the particle-consistent form agrees with the graph for one particle and is column-separable for several
+    fix = orc.SparseImageCodeEnergy(basis, patches, 0.01, cauchy, literal=False)
+    if n == 1:
+        np.testing.assert_allclose(fix.E(X), lit.E(X), rtol=1e-13)
+        np.testing.assert_allclose(fix.dEdX(X), lit.dEdX(X), rtol=1e-12, atol=1e-13)
+    else:
+        for b in range(n):
+            np.testing.assert_allclose(fix.E(X)[:, b], fix.E(X[:, b:b + 1])[:, 0], rtol=1e-13)
+            np.testing.assert_allclose(fix.dEdX(X)[:, b], fix.dEdX(X[:, b:b + 1])[:, 0], rtol=1e-12, atol=1e-13)

@@ -94,7 +94,7 @@ class FakeEngine(object):
     def ctx(self):
         return contextlib.nullcontext()
 
-    def launch(self, attempt0, n_iter, samples=None, it0=0, dwell=None, choice=None):
+    def launch(self, attempt0, n_iter, samples=None, it0=0, dwell=None, choice=None, energy=None):
         s = self.sampler
         fail = FakeEngine.script.pop(0) if FakeEngine.script else None
         FakeEngine.log.append(dict(attempt0=attempt0, n_iter=n_iter, it0=it0, eps=s.epsilon, L=s.num_leapfrog_steps,
