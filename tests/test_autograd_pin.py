@@ -118,3 +118,37 @@ def test_sparse_image_code_gradient_is_the_autodiff_of_the_reference_graph(cauch
         for b in range(n):
             np.testing.assert_allclose(fix.E(X)[:, b], fix.E(X[:, b:b + 1])[:, 0], rtol=1e-13)
             np.testing.assert_allclose(fix.dEdX(X)[:, b], fix.dEdX(X[:, b:b + 1])[:, 0], rtol=1e-12, atol=1e-13)
+
+
+def test_tf_fit_follows_autodiff_of_the_reference_graph_under_tf1_adam():
+    """search/objective.py:137-183 builds ``curve = exp(a t) cos(b t)``, ``loss = reduce_sum((y - curve)^2)`` and lets
+    ``tf.train.AdamOptimizer(learning_rate).minimize(loss)`` run.  TensorFlow is absent; the graph is written here in
+    torch, differentiated by autograd, and stepped with the update rule the TF1 documentation of AdamOptimizer states
+    (lr_t = lr sqrt(1 - b2^t) / (1 - b1^t); m, v moving averages; var -= lr_t m / (sqrt(v) + epsilon); b1 = 0.9,
+    b2 = 0.999, epsilon = 1e-8).  The package's tf_fit (numpy, analytic gradient) must walk the same path and return the
+    parameters of the smallest loss seen."""
+    from mjhmc_b200.search import objective
+    rs = np.random.RandomState(0)
+    t = np.linspace(0, 12, 60)
+    y = np.exp(-0.35 * t) * np.cos(0.9 * t) + 0.01 * rs.randn(60)
+    n_steps, lr = 300, 0.01
+    a0, b0 = objective.estimate_params(t, y)
+    params = torch.tensor([float(a0), float(b0)], dtype=torch.float64, requires_grad=True)
+    tt, yt = torch.tensor(t), torch.tensor(y)
+    m, v = torch.zeros(2, dtype=torch.float64), torch.zeros(2, dtype=torch.float64)
+    losses, trail = [], []
+    for step in range(1, n_steps + 1):
+        curve = torch.exp(params[0] * tt) * torch.cos(params[1] * tt)
+        loss = torch.sum((yt - curve) ** 2)
+        g, = torch.autograd.grad(loss, params)
+        losses.append(float(loss))
+        trail.append(params.detach().clone().numpy())
+        m = 0.9 * m + 0.1 * g
+        v = 0.999 * v + 0.001 * g * g
+        lr_t = lr * np.sqrt(1 - 0.999 ** step) / (1 - 0.9 ** step)
+        with torch.no_grad():
+            params -= lr_t * m / (torch.sqrt(v) + 1e-8)
+    want = trail[int(np.argmin(losses))]
+    got = objective.tf_fit(t, y, n_steps=n_steps, learning_rate=lr)
+    np.testing.assert_allclose(got, want, rtol=1e-10)
+    assert min(losses) < losses[0]
