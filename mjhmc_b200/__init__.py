@@ -11,15 +11,18 @@ __version__ = "0.1.0"
 
 
 def install_alias(name="mjhmc"):
-    from . import misc, samplers, search
+    from . import experiments, misc, samplers, search
+    from .experiments import spectral
     from .search import objective
-    from .misc import autocor, distributions, gen_mj_init, utils
+    from .misc import autocor, distributions, gen_mj_init, tf_distributions, utils
     from .samplers import hmc_state, markov_jump_hmc
     pkg = sys.modules[__name__]
     sys.modules[name] = pkg
     sys.modules[name + ".misc"] = misc
     sys.modules[name + ".misc.distributions"] = distributions
-    sys.modules[name + ".misc.tf_distributions"] = distributions      # Funnel's reference location
+    sys.modules[name + ".misc.tf_distributions"] = tf_distributions   # Funnel (re-exported), SparseImageCode
+    sys.modules[name + ".experiments"] = experiments
+    sys.modules[name + ".experiments.spectral"] = spectral
     sys.modules[name + ".misc.utils"] = utils
     sys.modules[name + ".misc.autocor"] = autocor
     sys.modules[name + ".misc.gen_mj_init"] = gen_mj_init
