@@ -77,6 +77,47 @@ __device__ __forceinline__ void leapfrog_L(const Dist& dist, T (&x)[D], T (&v)[D
 #endif
 }
 
+// Momentum refresh v = v sqrt(1 - beta) + z sqrt(beta) (hmc_state.py:121-129) for the lanes with `mine` set; called by
+// the whole warp.  PHILOX mode: the Box-Muller pairs of the refreshing lanes are shared out over all 32 lanes (job =
+// (refreshing lane, pair)) and handed back through shared memory -- one lane in seven takes an R move on the Funnel
+// of BASELINE config 5, and with every lane drawing its own D / 2 pairs the warp ran five Philox + log + sqrt +
+// sincospi passes at 15 % occupancy: 39 % of all instructions (profiles/r2_fused_funnel10d_cthmc_v0.txt).
+// Same counters, same arithmetic, same results as draw_normals.  zs: this CTA's [D][kFusedThreads] staging array.
+template <typename T, int D>
+__device__ __forceinline__ void refresh_momentum(const LaunchParams& p, long long i, unsigned long long attempt, int d,
+                                                 bool mine, T (&v)[D], T (*zs)[128]) {
+    const unsigned mask = __ballot_sync(0xffffffffu, mine);
+    if (mask == 0u) return;
+    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+    if (D <= 2 || p.rng_mode == MJHMC_RNG_INJECT) {          // one pair per lane: nothing to share out
+        if (mine) {
+            T z[D];
+            draw_normals<T, D>(p, i, attempt, d, z);
+#pragma unroll
+            for (int k = 0; k < D; ++k) v[k] = v[k] * (T)p.r_keep + z[k] * (T)p.r_mix;
+        }
+        return;
+    }
+    const int npairs = (d + 1) >> 1, njobs = __popc(mask) * npairs;
+    for (int job = lane; job < njobs; job += 32) {
+        const int r = job / npairs, pr = job - r * npairs;
+        const int owner = __fns(mask, 0, r + 1);                   // lane of the r-th refreshing particle
+        double z0, z1;
+        normal_pair(p, i - lane + owner, attempt, pr, d, z0, z1);
+        zs[2 * pr][wbase + owner] = (T)z0;
+        if (2 * pr + 1 < D) zs[2 * pr + 1][wbase + owner] = (2 * pr + 1 < d) ? (T)z1 : (T)0;
+    }
+    __syncwarp();
+    if (mine) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const T z = k < d ? zs[k][threadIdx.x] : (T)0;
+            v[k] = v[k] * (T)p.r_keep + z * (T)p.r_mix;
+        }
+    }
+    __syncwarp();
+}
+
 // FLF cache flags (one byte per particle).  bit0 is the reference's cache_active
 // (hmc_state.py:41-44,131-148: set by an L move, cleared by F and R moves).  bit1 says the
 // cached energy is valid; it is also set by an F move, because the FLF state of F z is F L z,
@@ -90,6 +131,7 @@ template <class Dist, typename T, int D>
 __global__ void __launch_bounds__(kFusedThreads, fused_min_blocks<T, D>())
 fused_sample_kernel(const __grid_constant__ LaunchParams p) {
     __shared__ int s_coin[2];          // batch-wide R coin of the discrete samplers, one draw per CTA
+    __shared__ T s_z[D][kFusedThreads];  // normals on their way from the lane that drew them to the lane that owns them
 
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < p.n;
@@ -128,6 +170,8 @@ fused_sample_kernel(const __grid_constant__ LaunchParams p) {
     for (int it = 0; it < p.n_iter; ++it) {
         const unsigned long long attempt = p.attempt0 + (unsigned long long)it;
         const bool active = live && !failed;
+        bool need_r = false;
+        unsigned int choice = 0;
         const T H = EX + EV;                                   // hmc_state.py:80-84
         T xt[D], vt[D], gt[D];
         T Hflf = Hc;
@@ -160,7 +204,6 @@ fused_sample_kernel(const __grid_constant__ LaunchParams p) {
             n_E += 1;
             n_exec += 1;
 
-            unsigned int choice = 0;
             if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
                 const Decision dc = decide_mj(p, i, attempt, (double)(H - Hl), (double)(H - Hflf));
                 if (dc.fail) { report_failure(p, it); failed = true; }
@@ -178,11 +221,7 @@ fused_sample_kernel(const __grid_constant__ LaunchParams p) {
                         Hc = Hl; cflags = kCacheValid;              // :410 clears cache_active; FLF(F z) = F L z
                         n_f += 1;
                     } else {
-                        T z[D];
-                        draw_normals<T, D>(p, i, attempt, d, z);
-#pragma unroll
-                        for (int k = 0; k < D; ++k) v[k] = v[k] * (T)p.r_keep + z[k] * (T)p.r_mix;   // hmc_state.py:126
-                        EV = kinetic<T, D>(v);
+                        need_r = true;                              // refreshed below, by the whole warp
                         cflags = 0;                                 // :409
                         n_r += 1;
                     }
@@ -203,11 +242,7 @@ fused_sample_kernel(const __grid_constant__ LaunchParams p) {
                         for (int k = 0; k < D; ++k) v[k] = -v[k];
                         n_f += 1;
                     } else {
-                        T z[D];
-                        draw_normals<T, D>(p, i, attempt, d, z);
-#pragma unroll
-                        for (int k = 0; k < D; ++k) v[k] = v[k] * (T)p.r_keep + z[k] * (T)p.r_mix;
-                        EV = kinetic<T, D>(v);
+                        need_r = true;
                         n_r += 1;
                     }
                 }
@@ -225,11 +260,7 @@ fused_sample_kernel(const __grid_constant__ LaunchParams p) {
                     for (int k = 0; k < D; ++k) v[k] = -v[k];
                 }
                 if (choice & 4u) {                                  // one coin for the whole batch :138
-                    T z[D];
-                    draw_normals<T, D>(p, i, attempt, d, z);
-#pragma unroll
-                    for (int k = 0; k < D; ++k) v[k] = v[k] * (T)p.r_keep + z[k] * (T)p.r_mix;
-                    EV = kinetic<T, D>(v);
+                    need_r = true;
                     n_r += 1;
                 }
                 n_l += (acc && flip);
@@ -237,6 +268,11 @@ fused_sample_kernel(const __grid_constant__ LaunchParams p) {
                 n_fl += (acc && !flip);
             }
 
+        }
+        // ---- R moves: V = V sqrt(1 - beta) + randn sqrt(beta) (hmc_state.py:126), shared by the warp
+        refresh_momentum<T, D>(p, i, attempt, d, need_r, v, s_z);
+        if (need_r) EV = kinetic<T, D>(v);
+        if (active) {
             if (!failed) {
                 // ---- record (markov_jump_hmc.py:169,334)
                 if (p.samples) {

@@ -3,7 +3,7 @@
 out=$1; shift
 : > "$out"
 for w in "$@"; do
-  python bench.py --workload "$w" --steps 10 --warmup 3 --no-cpu-baseline >> "$out" 2>> "${out%.jsonl}.err" || echo "{\"workload\": \"$w\", \"failed\": true}" >> "$out"
+  python bench.py --workload "$w" --steps 10 --warmup 3 --no-cpu-baseline --no-secondary >> "$out" 2>> "${out%.jsonl}.err" || echo "{\"workload\": \"$w\", \"failed\": true}" >> "$out"
 done
 python - "$out" <<'PY'
 import json, sys
