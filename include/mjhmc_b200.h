@@ -94,9 +94,15 @@ typedef struct mjhmc_hp {
 /* random stream (DESIGN.md "Random streams"): counter-based Philox4x32-10, or
  * pre-drawn arrays indexed (attempt, slot, particle) for trajectory parity with
  * the reference's np.random call sites (hmc_state.py:126; markov_jump_hmc.py:125,132,138; utils.py:42) */
+/* mjhmc_rng.flags.  LITERAL_RACE: evaluate all three exponential holding times of the continuous-time samplers in
+ * fp64 exactly as misc/utils.py:15-49 writes them.  Default (0): the kernels first enclose the three times in
+ * single-precision intervals and evaluate only the winner in fp64 when the intervals separate (csrc/common.cuh);
+ * the choices and the stored holding times are bit-identical either way (tests/test_gpu_screen.py compares them). */
+#define MJHMC_RNG_FLAG_LITERAL_RACE 1
+
 typedef struct mjhmc_rng {
     int32_t  mode;              /* MJHMC_RNG_* */
-    int32_t  _pad;
+    int32_t  flags;             /* MJHMC_RNG_FLAG_* */
     uint64_t seed;              /* PHILOX key */
     uint64_t attempt0;          /* attempt index of the first iteration of this launch */
     uint64_t particle0;         /* global index of local particle 0 (shard offset) */

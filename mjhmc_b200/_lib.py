@@ -15,6 +15,7 @@ DIST_TEST_GAUSSIAN, DIST_DIAG_GAUSSIAN, DIST_ROUGH_WELL, DIST_FUNNEL, DIST_FUNNE
     DIST_DENSE_GAUSSIAN, DIST_PRODUCT_OF_T, DIST_MULTIMODAL = range(8)
 SAMPLER_DISCRETE, SAMPLER_CONTINUOUS_TIME, SAMPLER_MARKOV_JUMP = range(3)
 RNG_PHILOX, RNG_INJECT = 0, 1
+RNG_FLAG_LITERAL_RACE = 1
 CNT_L, CNT_F, CNT_FL, CNT_R, CNT_E, CNT_DEDX, CNT_FAIL, CNT_EXEC = range(8)
 N_COUNTERS = 8
 COUNTER_STRIPES = 32
@@ -35,7 +36,7 @@ class HP(C.Structure):
 
 
 class RNG(C.Structure):
-    _fields_ = [("mode", C.c_int32), ("_pad", C.c_int32), ("seed", C.c_uint64), ("attempt0", C.c_uint64),
+    _fields_ = [("mode", C.c_int32), ("flags", C.c_int32), ("seed", C.c_uint64), ("attempt0", C.c_uint64),
                 ("particle0", C.c_uint64), ("Z", C.c_void_p), ("U", C.c_void_p), ("U0", C.c_void_p),
                 ("inj_ld", C.c_int64)]
 

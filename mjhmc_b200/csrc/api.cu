@@ -68,6 +68,7 @@ static int fill_hp(LaunchParams& p, const mjhmc_hp* hp) {
 
 static int fill_rng(LaunchParams& p, const mjhmc_rng* rng) {
     p.rng_mode = rng->mode;
+    p.rng_flags = rng->flags;
     p.seed = rng->seed;
     p.attempt0 = rng->attempt0;
     p.particle0 = rng->particle0;

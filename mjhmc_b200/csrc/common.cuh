@@ -33,7 +33,7 @@ struct LaunchParams {
     int sampler, L, n_iter, d;
     double eps, p_flip, p_r, r_keep, r_mix;   // r_keep = sqrt(1-beta), r_mix = sqrt(beta)
     // rng
-    int rng_mode;
+    int rng_mode, rng_flags;
     unsigned long long seed, attempt0, particle0;
     const double* Z; const double* U; const double* U0; long long inj_ld;
     // distribution
@@ -162,10 +162,101 @@ __device__ __forceinline__ Decision decide_mj_u(double p_r, double u0, double u1
     if (tr < dc.dwell) { dc.choice = 2; dc.dwell = tr; }
     return dc;
 }
+// ---- certified single-precision screening of the holding-time race
+// The operator choice is the index of the first minimum of three exponential draws (1/rate) * -log(1 - u)
+// (utils.py:15-49).  Evaluated literally that is three fp64 logs, three fp64 divisions and an fp64 exp + sqrt per
+// rate: ~400 instructions, 40 % of the Funnel / ContinuousTimeHMC kernel of BASELINE config 5
+// (profiles/r2_fused_funnel10d_cthmc_v1_shared_refresh.txt).  Only the ORDER of the three times decides the move, and only the
+// winner's time is ever stored.  So each time is first enclosed in a single-precision interval [lo, hi] with a
+// rigorous error budget (MUFU lg2 / ex2 / rcp, ~60 instructions); where the intervals separate, the choice is the
+// one the fp64 code would make, and the winner's time -- if the caller stores it -- is evaluated with exactly the
+// reference expression.  Where they overlap (a few lanes in 1e5), the literal fp64 code decides (decide_*_u).
+// Error budgets (all bounds hold for the fp64 VALUES the literal code computes, which differ from the exact real
+// numbers by < 1e-15 relative, far inside the slack):
+//   w = -log(1 - u):  x = float(1 - u) carries 2^-24 relative error (|dw| <= 6e-8); __logf: absolute error
+//       2^-21.41 for x in [0.5, 2], 3 ulp otherwise  =>  |w~ - w| <= 6e-7 (1 + w~).
+//   r = sqrt(exp(e)), |e| <= 64:  a = float(e log2(e) / 2), |da| <= 46.2 * 2^-24 => 1.9e-6 relative in 2^a;
+//       ex2.approx 2^-22  =>  |r~ / r - 1| <= 2.2e-6, enclosed with 4e-6.  e < -64: r in [0, 1.3e-14].
+//       e > 64 or NaN: not screened (the literal code also detects the non-finite rate, utils.py:41-48).
+//   t = w / r:  __fdividef 2 ulp, every product with (1 +- 1e-6) absorbs the fp32 roundings of the step.
+struct Encl { float lo, hi; };
+
+__device__ __forceinline__ Encl encl_neg_log1m(double u) {
+    const float x = __double2float_rn(1.0 - u);
+    const float w = -__logf(x);
+    const float e = fmaf(w, 6e-7f, 6e-7f);
+    Encl r; r.lo = fmaxf(w - e, 0.0f); r.hi = w + e;
+    return r;
+}
+__device__ __forceinline__ bool encl_jump_rate(double ediff, Encl& r) {
+    if (!(ediff <= 64.0)) return false;
+    if (ediff < -64.0) { r.lo = 0.0f; r.hi = 1.3e-14f; return true; }      // exp(-32) = 1.27e-14
+    const float a = __double2float_rn(ediff * 0.72134752044448170368);      // log2(e) / 2
+    float v;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(a));
+    r.lo = v * (1.0f - 4e-6f); r.hi = v * (1.0f + 4e-6f);
+    return true;
+}
+__device__ __forceinline__ Encl encl_time(Encl w, Encl r) {
+    Encl t;
+    t.lo = r.hi > 0.0f ? __fdividef(w.lo, r.hi) * (1.0f - 1e-6f) : INFINITY;
+    t.hi = r.lo > 0.0f ? __fdividef(w.hi, r.lo) * (1.0f + 1e-6f) : INFINITY;
+    return t;
+}
+// p_r is a launch constant; screened only inside a range where float(p_r) and __fdividef are harmless
+__device__ __forceinline__ bool encl_refresh_time(double p_r, double u2, Encl& t) {
+    if (p_r == 0.0) { t.lo = t.hi = INFINITY; return true; }                // exp_draw: zero rate -> inf
+    if (!(p_r >= 1e-30 && p_r <= 1e30)) return false;
+    const float pf = __double2float_rn(p_r);
+    Encl r; r.lo = pf * (1.0f - 1e-6f); r.hi = pf * (1.0f + 1e-6f);
+    t = encl_time(encl_neg_log1m(u2), r);
+    return true;
+}
+// index of the first minimum of (a, b, c) the way min_idx finds it (a strict `<` replaces the incumbent), or -1 when
+// the enclosures do not decide
+__device__ __forceinline__ int certain_first_min(Encl a, Encl b, Encl c) {
+    if (b.lo > a.hi && c.lo > a.hi) return 0;
+    if (b.hi < a.lo && c.lo > b.hi) return 1;
+    if (c.hi < a.lo && c.hi < b.lo) return 2;
+    return -1;
+}
+
+// need_dwell: the caller stores the holding time of this attempt (dwelling-time record or the last iteration of a
+// launch); otherwise only the choice is produced.
+__device__ __forceinline__ Decision decide_mj_screened(double p_r, double u0, double u1, double u2,
+                                                       double ediff_l, double ediff_flf, bool need_dwell,
+                                                       bool literal) {
+#ifndef MJ_NO_SCREEN
+    Encl rl, rflf, tr;
+    if (!literal && encl_jump_rate(ediff_l, rl) && encl_jump_rate(ediff_flf, rflf) && encl_refresh_time(p_r, u2, tr)) {
+        Encl rf;                                                           // rflf - min(rl, rflf) = max(rflf - rl, 0)
+        rf.lo = fmaxf(rflf.lo - rl.hi, 0.0f) * (1.0f - 1e-6f);
+        rf.hi = fmaxf(rflf.hi - rl.lo, 0.0f) * (1.0f + 1e-6f);
+        const Encl tl = encl_time(encl_neg_log1m(u0), rl);
+        const Encl tf = encl_time(encl_neg_log1m(u1), rf);
+        const int c = certain_first_min(tl, tf, tr);
+        if (c >= 0) {
+            Decision dc; dc.choice = (unsigned int)c; dc.dwell = 0.0; dc.fail = false;
+            if (need_dwell) {
+                double rate = p_r, u = u2;
+                if (c != 2) {
+                    const double erl = jump_rate(ediff_l);
+                    rate = erl; u = u0;
+                    if (c == 1) { const double erflf = jump_rate(ediff_flf); rate = erflf - (erl < erflf ? erl : erflf); u = u1; }
+                }
+                dc.dwell = exp_draw(rate, u);
+            }
+            return dc;
+        }
+    }
+#endif
+    return decide_mj_u(p_r, u0, u1, u2, ediff_l, ediff_flf);
+}
 MJ_COLD Decision decide_mj(const LaunchParams& p, long long i, unsigned long long attempt,
-                                              double ediff_l, double ediff_flf) {
+                           double ediff_l, double ediff_flf, bool need_dwell) {
     const Uniform3 u = draw_uniforms(p, i, attempt, p.p_r != 0.0);
-    return decide_mj_u(p.p_r, u.u0, u.u1, u.u2, ediff_l, ediff_flf);
+    return decide_mj_screened(p.p_r, u.u0, u.u1, u.u2, ediff_l, ediff_flf, need_dwell,
+                              (p.rng_flags & MJHMC_RNG_FLAG_LITERAL_RACE) != 0);
 }
 
 // ContinuousTimeHMC (markov_jump_hmc.py:261-275): choice 0 = F, 1 = FL, 2 = R.
@@ -181,10 +272,33 @@ __device__ __forceinline__ Decision decide_ct_u(double p_r, double u0, double u1
     if (tr < dc.dwell) { dc.choice = 2; dc.dwell = tr; }
     return dc;
 }
+__device__ __forceinline__ Decision decide_ct_screened(double p_r, double u0, double u1, double u2,
+                                                       double ediff_fl, bool need_dwell, bool literal) {
+#ifndef MJ_NO_SCREEN
+    Encl rfl, tr;
+    if (!literal && encl_jump_rate(ediff_fl, rfl) && encl_refresh_time(p_r, u2, tr)) {
+        const Encl tf = encl_neg_log1m(u1);                                // rate 1: (1.0 / 1.0) * w
+        const Encl tfl = encl_time(encl_neg_log1m(u0), rfl);
+        const int c = certain_first_min(tf, tfl, tr);
+        if (c >= 0) {
+            Decision dc; dc.choice = (unsigned int)c; dc.dwell = 0.0; dc.fail = false;
+            if (need_dwell) {
+                double rate = 1.0, u = u1;
+                if (c == 1) { rate = jump_rate(ediff_fl); u = u0; }
+                if (c == 2) { rate = p_r; u = u2; }
+                dc.dwell = exp_draw(rate, u);
+            }
+            return dc;
+        }
+    }
+#endif
+    return decide_ct_u(p_r, u0, u1, u2, ediff_fl);
+}
 MJ_COLD Decision decide_ct(const LaunchParams& p, long long i, unsigned long long attempt,
-                                              double ediff_fl) {
+                           double ediff_fl, bool need_dwell) {
     const Uniform3 u = draw_uniforms(p, i, attempt, p.p_r != 0.0);
-    return decide_ct_u(p.p_r, u.u0, u.u1, u.u2, ediff_fl);
+    return decide_ct_screened(p.p_r, u.u0, u.u1, u.u2, ediff_fl, need_dwell,
+                              (p.rng_flags & MJHMC_RNG_FLAG_LITERAL_RACE) != 0);
 }
 
 // HMCBase / HMC / ControlHMC (markov_jump_hmc.py:106-148): bit0 = FL accepted, bit1 = flipped,
@@ -214,46 +328,15 @@ MJ_COLD Decision decide_discrete(const LaunchParams& p, long long i, unsigned lo
     return dc;
 }
 
-// Streaming-kernel forms.  The exponential draws are (1/rate) * w with w = -log(1 - u) (exp_draw above): w
-// depends on the uniforms only, so the kernel evaluates the three logs BEFORE the trajectory / the energy
-// reduction (draw_log_uniforms) and only the rate-dependent half stays on the critical path.  Same operations,
-// same operands, same results as decide_mj_u / decide_ct_u.
-struct LogUniform3 { double w0, w1, w2; };
-static __device__ __noinline__ LogUniform3 neg_log1m3(double u0, double u1, double u2, bool need_u2) {
-    LogUniform3 w;
-    w.w0 = -log(1.0 - u0);
-    w.w1 = -log(1.0 - u1);
-    w.w2 = need_u2 ? -log(1.0 - u2) : 0.0;
-    return w;
+// Streaming-kernel forms: the uniforms are drawn before the trajectory (the Philox rounds overlap the fp64 work),
+// the decision runs out of line once the energies are known.
+static __device__ __noinline__ Decision decide_mj_s(double p_r, double u0, double u1, double u2,
+                                                    double ediff_l, double ediff_flf, bool need_dwell, bool literal) {
+    return decide_mj_screened(p_r, u0, u1, u2, ediff_l, ediff_flf, need_dwell, literal);
 }
-__device__ __forceinline__ double exp_draw_w(double rate, double w) { return rate == 0.0 ? INFINITY : (1.0 / rate) * w; }
-
-static __device__ __noinline__ Decision decide_mj_w(double p_r, double w0, double w1, double w2,
-                                                    double ediff_l, double ediff_flf) {
-    Decision dc; dc.choice = 0; dc.dwell = 0.0; dc.fail = false;
-    const double rl = jump_rate(ediff_l);
-    const double rflf = jump_rate(ediff_flf);
-    if (!(isfinite(rl) && isfinite(rflf))) { dc.fail = true; return dc; }
-    const double rf = rflf - (rl < rflf ? rl : rflf);              // :368
-    const double tl = exp_draw_w(rl, w0);
-    const double tf = exp_draw_w(rf, w1);
-    const double tr = exp_draw_w(p_r, w2);
-    dc.dwell = tl;
-    if (tf < dc.dwell) { dc.choice = 1; dc.dwell = tf; }
-    if (tr < dc.dwell) { dc.choice = 2; dc.dwell = tr; }
-    return dc;
-}
-static __device__ __noinline__ Decision decide_ct_w(double p_r, double w0, double w1, double w2, double ediff_fl) {
-    Decision dc; dc.choice = 0; dc.dwell = 0.0; dc.fail = false;
-    const double rfl = jump_rate(ediff_fl);
-    if (!isfinite(rfl)) { dc.fail = true; return dc; }
-    const double tfl = exp_draw_w(rfl, w0);
-    const double tf = exp_draw_w(1.0, w1);
-    const double tr = exp_draw_w(p_r, w2);
-    dc.dwell = tf;
-    if (tfl < dc.dwell) { dc.choice = 1; dc.dwell = tfl; }
-    if (tr < dc.dwell) { dc.choice = 2; dc.dwell = tr; }
-    return dc;
+static __device__ __noinline__ Decision decide_ct_s(double p_r, double u0, double u1, double u2, double ediff_fl,
+                                                    bool need_dwell, bool literal) {
+    return decide_ct_screened(p_r, u0, u1, u2, ediff_fl, need_dwell, literal);
 }
 static __device__ __noinline__ unsigned int decide_discrete_s(double p_flip, double u0, double u1, double ediff,
                                                               bool coin_fired) {

@@ -304,7 +304,7 @@ dense_sample_kernel(const __grid_constant__ LaunchParams p) {
             unsigned int take = 0, flip = 0, refresh = 0, choice = 0;
             if (active) {
                 if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
-                    const Decision dc = decide_mj(p, ip, attempt, H - Hl, H - Hflf);
+                    const Decision dc = decide_mj(p, ip, attempt, H - Hl, H - Hflf, p.dwell != nullptr || (it + 1 == p.n_iter && p.dwell_last != nullptr));
                     if (dc.fail) { report_failure(p, it); failed = true; }
                     else {
                         choice = dc.choice; dwell = dc.dwell;
@@ -313,7 +313,7 @@ dense_sample_kernel(const __grid_constant__ LaunchParams p) {
                         else { refresh = 1; cflags = 0u; n_r += 1; }
                     }
                 } else if (sampler == MJHMC_SAMPLER_CONTINUOUS_TIME) {
-                    const Decision dc = decide_ct(p, ip, attempt, H - Hl);
+                    const Decision dc = decide_ct(p, ip, attempt, H - Hl, p.dwell != nullptr || (it + 1 == p.n_iter && p.dwell_last != nullptr));
                     if (dc.fail) { report_failure(p, it); failed = true; }
                     else {
                         choice = dc.choice; dwell = dc.dwell;

@@ -566,7 +566,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                     } else {
                         Hflf = Hcc[cur + tid];
                     }
-                    const Decision dc = decide_mj(p, cur + tid, attempt, (double)(H - Hl), (double)(H - Hflf));
+                    const Decision dc = decide_mj(p, cur + tid, attempt, (double)(H - Hl), (double)(H - Hflf), p.dwell != nullptr || (it + 1 == p.n_iter && p.dwell_last != nullptr));
                     if (dc.fail) report_failure(p, it);
                     else {
                         ok = 1; choice = dc.choice; dwell = dc.dwell;
@@ -578,7 +578,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                     p.ca_out[cur + tid] = (uint8_t)(ok ? cflags : (need ? (cflags & ~2u) : cflags));
                     ((float*)p.Hc_out)[cur + tid] = Hc;
                 } else if (sampler == MJHMC_SAMPLER_CONTINUOUS_TIME) {
-                    const Decision dc = decide_ct(p, cur + tid, attempt, (double)(H - Hl));
+                    const Decision dc = decide_ct(p, cur + tid, attempt, (double)(H - Hl), p.dwell != nullptr || (it + 1 == p.n_iter && p.dwell_last != nullptr));
                     if (dc.fail) report_failure(p, it);
                     else {
                         ok = 1; choice = dc.choice; dwell = dc.dwell;

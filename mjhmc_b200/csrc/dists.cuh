@@ -21,7 +21,48 @@ template <typename T> __device__ __forceinline__ T t_log(T x);
 template <> __device__ __forceinline__ double t_log<double>(double x) { return log(x); }
 template <> __device__ __forceinline__ float t_log<float>(float x) { return logf(x); }
 template <typename T> __device__ __forceinline__ T t_exp(T x);
-template <> __device__ __forceinline__ double t_exp<double>(double x) { return exp(x); }
+// exp(x) in fp64 for the leapfrog loop of the Funnel (tf_distributions.py:161-165: one exp per gradient): k = rint(x
+// log2 e) by the magic-number add, r = x - k ln 2 (two-term Cody-Waite with FMAs, |r| <= 0.3466), exp(r) by a degree-11
+// polynomial interpolated at Chebyshev nodes (truncation 1.6e-17 relative), 2^k added to the exponent field.  Maximum
+// error 0.6 ulp against mpmath (tools/probe/exp_poly_check.py).  The library exp() is the same scheme, but its
+// constants are literals that ptxas re-materialises with two UMOVs each on every call: 22 of its ~90 instructions,
+// 16 % of everything the Funnel kernel issued (profiles/r2_fused_funnel10d_cthmc_v1_shared_refresh.txt).  Here they are operands
+// read straight from the constant bank.  |x| >= 700 and NaN take the library path.
+static __constant__ double kExpC[15] = {
+    1.4426950408889634, -0.6931471805599453, -2.3190468138462996e-17,      // log2 e, -ln2 hi, -ln2 lo
+    1.0, 1.0, 0.5000000000000019, 0.1666666666666668, 0.04166666666648795, 0.008333333333319589,
+    0.0013888888952352863, 0.00019841269890076403, 2.4801485441561313e-05, 2.755724088722987e-06,
+    2.763265472252779e-07, 2.5110049204818658e-08};
+static __device__ __noinline__ double exp_out_of_range(double x) { return exp(x); }
+__device__ __forceinline__ double exp_poly(double x) {
+    const double magic = 6755399441055744.0;          // 1.5 * 2^52
+    const double t = fma(x, kExpC[0], magic);
+    const double k = t - magic;
+    double r = fma(k, kExpC[1], x);
+    r = fma(k, kExpC[2], r);
+    double s = kExpC[14];
+    s = fma(s, r, kExpC[13]);
+    s = fma(s, r, kExpC[12]);
+    s = fma(s, r, kExpC[11]);
+    s = fma(s, r, kExpC[10]);
+    s = fma(s, r, kExpC[9]);
+    s = fma(s, r, kExpC[8]);
+    s = fma(s, r, kExpC[7]);
+    s = fma(s, r, kExpC[6]);
+    s = fma(s, r, kExpC[5]);
+    s = fma(s, r, kExpC[4]);
+    s = fma(s, r, kExpC[3]);
+    double res = __hiloint2double(__double2hiint(s) + (__double2loint(t) << 20), __double2loint(s));
+    if (!(fabs(x) < 700.0)) res = exp_out_of_range(x);
+    return res;
+}
+template <> __device__ __forceinline__ double t_exp<double>(double x) {
+#ifdef MJ_LIB_EXP
+    return exp(x);
+#else
+    return exp_poly(x);
+#endif
+}
 template <> __device__ __forceinline__ float t_exp<float>(float x) { return expf(x); }
 
 // sin(pi u) for u in half-turns, branch free and table free (the fp64 leapfrog loop of RoughWell is
@@ -189,7 +230,10 @@ struct FunnelD {
         for (int k = 1; k < D; ++k) s += x[k] * x[k];
         return s;
     }
-    __device__ __forceinline__ void grad(const T (&x)[D], T (&g)[D]) const {
+    // grad returns exp(-x0): the energy at the end of a trajectory is asked for at the point of the last gradient
+    // (grad_aux / energy_after below), one exp per trajectory fewer
+    static constexpr bool kGradAux = true;
+    __device__ __forceinline__ T grad(const T (&x)[D], T (&g)[D]) const {
         const T e = t_exp<T>(-x[0]);
         const T s = sumsq(x);
         if (LITERAL) {
@@ -201,13 +245,14 @@ struct FunnelD {
 #pragma unroll
             for (int k = 1; k < D; ++k) g[k] = x[k] * e;
         }
+        return e;
     }
-    __device__ __forceinline__ T energy(const T (&x)[D]) const {
-        const T e = t_exp<T>(-x[0]);
+    __device__ __forceinline__ T energy_with(const T (&x)[D], T e) const {
         const T s = sumsq(x);
         if (LITERAL) return -(nk * x[0] * x[0] * inv_s2 + e * s);
         return x[0] * x[0] * ((T)0.5 * inv_s2) + (T)0.5 * e * s + (T)0.5 * nk * x[0];
     }
+    __device__ __forceinline__ T energy(const T (&x)[D]) const { return energy_with(x, t_exp<T>(-x[0])); }
 };
 
 // MultimodalGaussian (distributions.py:314-335): the separation vector is (2 sep, 0, ..., 0), so
@@ -235,5 +280,21 @@ struct MultimodalD {
         return -t_log<T>(t_exp<T>(-a) + t_exp<T>(-b));
     }
 };
+
+// Energies that share a transcendental with their gradient (Dist::kGradAux): grad returns it, energy_with takes it.
+template <class Dist, class = void> struct grad_has_aux { static constexpr bool value = false; };
+template <class Dist> struct grad_has_aux<Dist, decltype((void)Dist::kGradAux)> { static constexpr bool value = true; };
+
+template <class Dist, typename T, int D>
+__device__ __forceinline__ T grad_aux(const Dist& dist, const T (&x)[D], T (&g)[D]) {
+    if constexpr (grad_has_aux<Dist>::value) { return dist.grad(x, g); }
+    else { dist.grad(x, g); return (T)0; }
+}
+// energy at the point where the gradient that returned `aux` was evaluated
+template <class Dist, typename T, int D>
+__device__ __forceinline__ T energy_after(const Dist& dist, const T (&x)[D], T aux) {
+    if constexpr (grad_has_aux<Dist>::value) { return dist.energy_with(x, aux); }
+    else { return dist.energy(x); }
+}
 
 }  // namespace mjhmc

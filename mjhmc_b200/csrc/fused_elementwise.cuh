@@ -40,15 +40,17 @@ __device__ __forceinline__ T kinetic(const T (&v)[D]) {
     return s * (T)0.5;                       // hmc_state.py:49-50
 }
 
-// hmc_state.py:86-100 -- L leapfrog steps; g enters as dEdX(x) and leaves as dEdX(x').
+// hmc_state.py:86-100 -- L leapfrog steps; g enters as dEdX(x) and leaves as dEdX(x').  Returns what the last
+// gradient evaluation shares with the energy at x' (energy_after, dists.cuh).
 template <class Dist, typename T, int D>
-__device__ __forceinline__ void leapfrog_L(const Dist& dist, T (&x)[D], T (&v)[D], T (&g)[D],
-                                           T eps, T neg_half_eps, int L) {
+__device__ __forceinline__ T leapfrog_L(const Dist& dist, T (&x)[D], T (&v)[D], T (&g)[D],
+                                        T eps, T neg_half_eps, int L) {
+    T aux;
+    if (L <= 0) { T g0[D]; return grad_aux<Dist, T, D>(dist, x, g0); }
 #ifndef MJ_SPLIT_KICKS
     // the closing half kick of step s and the opening half kick of step s+1 use the same gradient: one full kick
     // (v - eps g instead of (v - eps/2 g) - eps/2 g: one rounding fewer, one fp64 FMA per dim and step fewer;
     // +5 % on the Funnel, neutral on RoughWell whose loop is the sine; -DMJ_SPLIT_KICKS restores the literal form)
-    if (L <= 0) return;
     const T neg_eps = neg_half_eps + neg_half_eps;
 #pragma unroll
     for (int k = 0; k < D; ++k) v[k] += neg_half_eps * g[k];
@@ -61,7 +63,7 @@ __device__ __forceinline__ void leapfrog_L(const Dist& dist, T (&x)[D], T (&v)[D
     }
 #pragma unroll
     for (int k = 0; k < D; ++k) x[k] += eps * v[k];
-    dist.grad(x, g);
+    aux = grad_aux<Dist, T, D>(dist, x, g);
 #pragma unroll
     for (int k = 0; k < D; ++k) v[k] += neg_half_eps * g[k];
 #else
@@ -70,11 +72,12 @@ __device__ __forceinline__ void leapfrog_L(const Dist& dist, T (&x)[D], T (&v)[D
         for (int k = 0; k < D; ++k) v[k] += neg_half_eps * g[k];
 #pragma unroll
         for (int k = 0; k < D; ++k) x[k] += eps * v[k];
-        dist.grad(x, g);
+        aux = grad_aux<Dist, T, D>(dist, x, g);
 #pragma unroll
         for (int k = 0; k < D; ++k) v[k] += neg_half_eps * g[k];
     }
 #endif
+    return aux;
 }
 
 // Momentum refresh v = v sqrt(1 - beta) + z sqrt(beta) (hmc_state.py:121-129) for the lanes with `mine` set; called by
@@ -172,6 +175,8 @@ fused_sample_kernel(const __grid_constant__ LaunchParams p) {
         const bool active = live && !failed;
         bool need_r = false;
         unsigned int choice = 0;
+        // the holding time is stored per iteration (dwelling-time record) or only after the last one (dwell_last)
+        const bool need_dwell = p.dwell != nullptr || (it + 1 == p.n_iter && p.dwell_last != nullptr);
         const T H = EX + EV;                                   // hmc_state.py:80-84
         T xt[D], vt[D], gt[D];
         T Hflf = Hc;
@@ -187,9 +192,9 @@ fused_sample_kernel(const __grid_constant__ LaunchParams p) {
                 if (!(cflags & kCacheValid)) {
 #pragma unroll
                     for (int k = 0; k < D; ++k) { xt[k] = x[k]; vt[k] = -v[k]; gt[k] = g[k]; }
-                    leapfrog_L<Dist, T, D>(dist, xt, vt, gt, eps, neg_half_eps, L);
+                    const T aux = leapfrog_L<Dist, T, D>(dist, xt, vt, gt, eps, neg_half_eps, L);
                     const T EVf = kinetic<T, D>(vt);
-                    const T EXf = dist.energy(xt);
+                    const T EXf = energy_after<Dist, T, D>(dist, xt, aux);
                     Hflf = EXf + EVf;
                     n_exec += 1;
                 }
@@ -197,15 +202,15 @@ fused_sample_kernel(const __grid_constant__ LaunchParams p) {
             // ---- L state (hmc_state.py:93-100)
 #pragma unroll
             for (int k = 0; k < D; ++k) { xt[k] = x[k]; vt[k] = v[k]; gt[k] = g[k]; }
-            leapfrog_L<Dist, T, D>(dist, xt, vt, gt, eps, neg_half_eps, L);
+            const T auxl = leapfrog_L<Dist, T, D>(dist, xt, vt, gt, eps, neg_half_eps, L);
             const T EVl = kinetic<T, D>(vt);
-            const T EXl = dist.energy(xt);
+            const T EXl = energy_after<Dist, T, D>(dist, xt, auxl);
             const T Hl = EXl + EVl;
             n_E += 1;
             n_exec += 1;
 
             if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
-                const Decision dc = decide_mj(p, i, attempt, (double)(H - Hl), (double)(H - Hflf));
+                const Decision dc = decide_mj(p, i, attempt, (double)(H - Hl), (double)(H - Hflf), need_dwell);
                 if (dc.fail) { report_failure(p, it); failed = true; }
                 else {
                     choice = dc.choice; dwell = dc.dwell;
@@ -228,7 +233,7 @@ fused_sample_kernel(const __grid_constant__ LaunchParams p) {
                 }
             } else if (sampler == MJHMC_SAMPLER_CONTINUOUS_TIME) {
                 // proposal is F L z (markov_jump_hmc.py:258)
-                const Decision dc = decide_ct(p, i, attempt, (double)(H - Hl));
+                const Decision dc = decide_ct(p, i, attempt, (double)(H - Hl), need_dwell);
                 if (dc.fail) { report_failure(p, it); failed = true; }
                 else {
                     choice = dc.choice; dwell = dc.dwell;

@@ -199,6 +199,7 @@ stream_sample_kernel(const __grid_constant__ LaunchParams p, const __grid_consta
     const T eps = (T)p.eps;
     const T neg_half_eps = (T)(-p.eps / 2.0);
     const int L = p.L, n_iter = p.n_iter;
+    const bool literal_race = (p.rng_flags & MJHMC_RNG_FLAG_LITERAL_RACE) != 0;
     const long long n = p.n, ld = p.ld;
     const bool use_tma = cfg.use_tma != 0;
     // G == 1: nothing couples the warps of a tile, so the stage is handed back by the last warp that leaves it
@@ -294,18 +295,15 @@ stream_sample_kernel(const __grid_constant__ LaunchParams p, const __grid_consta
                 __syncthreads();
             }
 
-            // the draws of this attempt do not depend on the trajectory: the Philox rounds and the three logs of
-            // the exponential holding times run on the integer / fp64 pipes before the energies are known
+            // the draws of this attempt do not depend on the trajectory: the Philox rounds run on the integer pipe
+            // before the energies are known
             double u0 = 0.0, u1 = 0.0, u2 = 0.0;
             if (decider && active) {
                 const bool need_u2 = !DISCRETE && p.p_r != 0.0;
                 const Uniform3 u = draw_uniforms(p, i, attempt, need_u2);
                 u0 = u.u0; u1 = u.u1; u2 = u.u2;
-                if (!DISCRETE) {
-                    const LogUniform3 w = neg_log1m3(u0, u1, u2, need_u2);
-                    u0 = w.w0; u1 = w.w1; u2 = w.w2;
-                }
             }
+            const bool need_dwell = !DISCRETE && (p.dwell != nullptr || (last && p.dwell_last != nullptr));
 
             T exf = (T)0, evf = (T)0, exl = (T)0, evl = (T)0;
             if (active) {
@@ -352,7 +350,7 @@ stream_sample_kernel(const __grid_constant__ LaunchParams p, const __grid_consta
                     T Hflf = Hc;
                     if (!(cflags & kCacheRef)) n_E += 1;           // the reference evaluates the FLF state here
                     if (!(cflags & kCacheValid)) { Hflf = Hf; n_exec += 1; }
-                    const Decision dc = decide_mj_w(p.p_r, u0, u1, u2, (double)(H - Hl), (double)(H - Hflf));
+                    const Decision dc = decide_mj_s(p.p_r, u0, u1, u2, (double)(H - Hl), (double)(H - Hflf), need_dwell, literal_race);
                     if (dc.fail) { report_failure(p, it); failed = true; }
                     else {
                         choice = dc.choice; dwell = dc.dwell;
@@ -361,7 +359,7 @@ stream_sample_kernel(const __grid_constant__ LaunchParams p, const __grid_consta
                         else { cflags = 0; n_r += 1; }                                                // :409
                     }
                 } else if (CT) {
-                    const Decision dc = decide_ct_w(p.p_r, u0, u1, u2, (double)(H - Hl));
+                    const Decision dc = decide_ct_s(p.p_r, u0, u1, u2, (double)(H - Hl), need_dwell, literal_race);
                     if (dc.fail) { report_failure(p, it); failed = true; }
                     else {
                         choice = dc.choice; dwell = dc.dwell;

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kThreads) transition_kernel(const __grid_const
         if (p.sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
             uint8_t* ca = p.ca_out; T* Hc = (T*)p.Hc_out;
             const T Hflf = ca[i] ? Hc[i] : H_flf[i];
-            const Decision dc = decide_mj(p, i, attempt, (double)(H - Hl), (double)(H - Hflf));
+            const Decision dc = decide_mj(p, i, attempt, (double)(H - Hl), (double)(H - Hflf), p.dwell != nullptr || p.dwell_last != nullptr);
             if (dc.fail) { report_failure(p, 0); failed = true; }
             else {
                 choice = dc.choice; dwell = dc.dwell;
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kThreads) transition_kernel(const __grid_const
                 else { refresh = true; ca[i] = 0; n_r = 1; }
             }
         } else if (p.sampler == MJHMC_SAMPLER_CONTINUOUS_TIME) {
-            const Decision dc = decide_ct(p, i, attempt, (double)(H - Hl));
+            const Decision dc = decide_ct(p, i, attempt, (double)(H - Hl), p.dwell != nullptr || p.dwell_last != nullptr);
             if (dc.fail) { report_failure(p, 0); failed = true; }
             else {
                 choice = dc.choice; dwell = dc.dwell;

@@ -32,6 +32,8 @@ class HMCState(object):
         st.active_idx = np.arange(st.nbatch)
         st.cache_active = np.zeros(st.nbatch, dtype=bool) if cache_active is None else cache_active
         st.H_cache = np.zeros(st.nbatch) if H_cache is None else H_cache
+        # an empty FLF cache is cleared on the device instead of being uploaded (the arrays above stay readable)
+        st._empty_cache = cache_active is None and H_cache is None
         return st
 
     # derived arrays (hmc_state.py:28-39, 46-53), evaluated on the device, not counted

@@ -41,7 +41,7 @@ INFINITE_RATE_MSG = ("Infinite rate. This occurs when calculating transition rat
                      "Try decreasing the leapfrog stepsize/number of steps or dividing "
                      " the energy by a large constant.")
 
-_B200_KWARGS = ("dtype", "seed", "device", "injected_draws", "particle_offset", "V", "kernel", "sharded")
+_B200_KWARGS = ("dtype", "seed", "device", "injected_draws", "particle_offset", "V", "kernel", "sharded", "literal_race")
 
 
 class _CallableEnergy(Distribution):
@@ -87,6 +87,9 @@ class _Engine(object):
         self.code = _device.dtype_code(self.dtype)
         self.d, self.n = X0.shape
         self.offset = int(opts.get("particle_offset") or 0)
+        # B200 extension (testing aid): evaluate the three holding times of every attempt literally in fp64 instead of
+        # screening the race in single precision first (include/mjhmc_b200.h MJHMC_RNG_FLAG_LITERAL_RACE)
+        self.literal_race = bool(opts.get("literal_race"))
         inj = opts.get("injected_draws")
         self.inj = None
         if inj is not None:
@@ -158,6 +161,7 @@ class _Engine(object):
         r.seed = self.seed
         r.attempt0 = int(attempt0)
         r.particle0 = self.offset
+        r.flags = _lib.RNG_FLAG_LITERAL_RACE if self.literal_race else 0
         if self.inj is not None:
             r.mode = _lib.RNG_INJECT
             r.Z = self.inj["Z"].data_ptr() if self.inj["Z"] is not None else None
@@ -344,10 +348,17 @@ class _Engine(object):
 
     def upload(self, st):
         c = self.cur
-        self.X[c].copy_(_device.to_device(st.X, self.dtype, self.device))
-        self.V[c].copy_(_device.to_device(st.V, self.dtype, self.device))
-        self.ca[c].copy_(torch.as_tensor(np.asarray(st.cache_active, dtype=np.uint8) * 3, device=self.device))
-        self.Hc[c].copy_(_device.to_device(st.H_cache, self.dtype, self.device))
+        for dst, src in ((self.X[c], st.X), (self.V[c], st.V)):
+            if isinstance(src, torch.Tensor) and src.dtype == dst.dtype and src.is_pinned() and src.shape == dst.shape:
+                dst.copy_(src, non_blocking=True)           # pinned host buffer: one async H2D, no staging copy
+            else:
+                dst.copy_(_device.to_device(src, self.dtype, self.device))
+        if getattr(st, "_empty_cache", False):
+            self.ca[c].zero_()
+            self.Hc[c].zero_()
+        else:
+            self.ca[c].copy_(torch.as_tensor(np.asarray(st.cache_active, dtype=np.uint8) * 3, device=self.device))
+            self.Hc[c].copy_(_device.to_device(st.H_cache, self.dtype, self.device))
         self._cache_key = None
         if not self.fused:
             self.G = self._callback(self.X[0], True, count=False)
