@@ -99,6 +99,10 @@ typedef struct mjhmc_hp {
  * single-precision intervals and evaluate only the winner in fp64 when the intervals separate (csrc/common.cuh);
  * the choices and the stored holding times are bit-identical either way (tests/test_gpu_screen.py compares them). */
 #define MJHMC_RNG_FLAG_LITERAL_RACE 1
+/* REGISTER_STATE: run the register-resident form of the fused kernel also where the library would keep the particle
+ * state in shared memory between trajectories (ndims >= 6, csrc/fused_elementwise.cuh: fused_stash_kernel).  Same
+ * results bit for bit; the flag exists so the tests can compare the two. */
+#define MJHMC_RNG_FLAG_REGISTER_STATE 2
 
 typedef struct mjhmc_rng {
     int32_t  mode;              /* MJHMC_RNG_* */

@@ -15,7 +15,7 @@ DIST_TEST_GAUSSIAN, DIST_DIAG_GAUSSIAN, DIST_ROUGH_WELL, DIST_FUNNEL, DIST_FUNNE
     DIST_DENSE_GAUSSIAN, DIST_PRODUCT_OF_T, DIST_MULTIMODAL = range(8)
 SAMPLER_DISCRETE, SAMPLER_CONTINUOUS_TIME, SAMPLER_MARKOV_JUMP = range(3)
 RNG_PHILOX, RNG_INJECT = 0, 1
-RNG_FLAG_LITERAL_RACE = 1
+RNG_FLAG_LITERAL_RACE, RNG_FLAG_REGISTER_STATE = 1, 2
 CNT_L, CNT_F, CNT_FL, CNT_R, CNT_E, CNT_DEDX, CNT_FAIL, CNT_EXEC = range(8)
 N_COUNTERS = 8
 COUNTER_STRIPES = 32

@@ -221,20 +221,30 @@ __device__ __forceinline__ int certain_first_min(Encl a, Encl b, Encl c) {
     return -1;
 }
 
+// The part of the screen that depends on the uniforms only (the streaming kernel evaluates it before the trajectory,
+// where it fills latency slots; after the energies meet only the rates, three divisions and the comparisons remain).
+struct RaceDraws { Encl w0, w1, tr; bool ok; };
+__device__ __forceinline__ RaceDraws race_draws(double p_r, double u0, double u1, double u2, bool literal) {
+    RaceDraws rd;
+    rd.w0 = encl_neg_log1m(u0);
+    rd.w1 = encl_neg_log1m(u1);
+    rd.ok = !literal && encl_refresh_time(p_r, u2, rd.tr);
+    return rd;
+}
+
 // need_dwell: the caller stores the holding time of this attempt (dwelling-time record or the last iteration of a
 // launch); otherwise only the choice is produced.
-__device__ __forceinline__ Decision decide_mj_screened(double p_r, double u0, double u1, double u2,
-                                                       double ediff_l, double ediff_flf, bool need_dwell,
-                                                       bool literal) {
+__device__ __forceinline__ Decision decide_mj_screened(double p_r, double u0, double u1, double u2, const RaceDraws& rd,
+                                                       double ediff_l, double ediff_flf, bool need_dwell) {
 #ifndef MJ_NO_SCREEN
-    Encl rl, rflf, tr;
-    if (!literal && encl_jump_rate(ediff_l, rl) && encl_jump_rate(ediff_flf, rflf) && encl_refresh_time(p_r, u2, tr)) {
+    Encl rl, rflf;
+    if (rd.ok && encl_jump_rate(ediff_l, rl) && encl_jump_rate(ediff_flf, rflf)) {
         Encl rf;                                                           // rflf - min(rl, rflf) = max(rflf - rl, 0)
         rf.lo = fmaxf(rflf.lo - rl.hi, 0.0f) * (1.0f - 1e-6f);
         rf.hi = fmaxf(rflf.hi - rl.lo, 0.0f) * (1.0f + 1e-6f);
-        const Encl tl = encl_time(encl_neg_log1m(u0), rl);
-        const Encl tf = encl_time(encl_neg_log1m(u1), rf);
-        const int c = certain_first_min(tl, tf, tr);
+        const Encl tl = encl_time(rd.w0, rl);
+        const Encl tf = encl_time(rd.w1, rf);
+        const int c = certain_first_min(tl, tf, rd.tr);
         if (c >= 0) {
             Decision dc; dc.choice = (unsigned int)c; dc.dwell = 0.0; dc.fail = false;
             if (need_dwell) {
@@ -255,8 +265,8 @@ __device__ __forceinline__ Decision decide_mj_screened(double p_r, double u0, do
 MJ_COLD Decision decide_mj(const LaunchParams& p, long long i, unsigned long long attempt,
                            double ediff_l, double ediff_flf, bool need_dwell) {
     const Uniform3 u = draw_uniforms(p, i, attempt, p.p_r != 0.0);
-    return decide_mj_screened(p.p_r, u.u0, u.u1, u.u2, ediff_l, ediff_flf, need_dwell,
-                              (p.rng_flags & MJHMC_RNG_FLAG_LITERAL_RACE) != 0);
+    const RaceDraws rd = race_draws(p.p_r, u.u0, u.u1, u.u2, (p.rng_flags & MJHMC_RNG_FLAG_LITERAL_RACE) != 0);
+    return decide_mj_screened(p.p_r, u.u0, u.u1, u.u2, rd, ediff_l, ediff_flf, need_dwell);
 }
 
 // ContinuousTimeHMC (markov_jump_hmc.py:261-275): choice 0 = F, 1 = FL, 2 = R.
@@ -272,14 +282,13 @@ __device__ __forceinline__ Decision decide_ct_u(double p_r, double u0, double u1
     if (tr < dc.dwell) { dc.choice = 2; dc.dwell = tr; }
     return dc;
 }
-__device__ __forceinline__ Decision decide_ct_screened(double p_r, double u0, double u1, double u2,
-                                                       double ediff_fl, bool need_dwell, bool literal) {
+__device__ __forceinline__ Decision decide_ct_screened(double p_r, double u0, double u1, double u2, const RaceDraws& rd,
+                                                       double ediff_fl, bool need_dwell) {
 #ifndef MJ_NO_SCREEN
-    Encl rfl, tr;
-    if (!literal && encl_jump_rate(ediff_fl, rfl) && encl_refresh_time(p_r, u2, tr)) {
-        const Encl tf = encl_neg_log1m(u1);                                // rate 1: (1.0 / 1.0) * w
-        const Encl tfl = encl_time(encl_neg_log1m(u0), rfl);
-        const int c = certain_first_min(tf, tfl, tr);
+    Encl rfl;
+    if (rd.ok && encl_jump_rate(ediff_fl, rfl)) {
+        const Encl tfl = encl_time(rd.w0, rfl);
+        const int c = certain_first_min(rd.w1, tfl, rd.tr);               // rate 1: t_f = (1.0 / 1.0) * w1
         if (c >= 0) {
             Decision dc; dc.choice = (unsigned int)c; dc.dwell = 0.0; dc.fail = false;
             if (need_dwell) {
@@ -297,8 +306,8 @@ __device__ __forceinline__ Decision decide_ct_screened(double p_r, double u0, do
 MJ_COLD Decision decide_ct(const LaunchParams& p, long long i, unsigned long long attempt,
                            double ediff_fl, bool need_dwell) {
     const Uniform3 u = draw_uniforms(p, i, attempt, p.p_r != 0.0);
-    return decide_ct_screened(p.p_r, u.u0, u.u1, u.u2, ediff_fl, need_dwell,
-                              (p.rng_flags & MJHMC_RNG_FLAG_LITERAL_RACE) != 0);
+    const RaceDraws rd = race_draws(p.p_r, u.u0, u.u1, u.u2, (p.rng_flags & MJHMC_RNG_FLAG_LITERAL_RACE) != 0);
+    return decide_ct_screened(p.p_r, u.u0, u.u1, u.u2, rd, ediff_fl, need_dwell);
 }
 
 // HMCBase / HMC / ControlHMC (markov_jump_hmc.py:106-148): bit0 = FL accepted, bit1 = flipped,
@@ -330,13 +339,13 @@ MJ_COLD Decision decide_discrete(const LaunchParams& p, long long i, unsigned lo
 
 // Streaming-kernel forms: the uniforms are drawn before the trajectory (the Philox rounds overlap the fp64 work),
 // the decision runs out of line once the energies are known.
-static __device__ __noinline__ Decision decide_mj_s(double p_r, double u0, double u1, double u2,
-                                                    double ediff_l, double ediff_flf, bool need_dwell, bool literal) {
-    return decide_mj_screened(p_r, u0, u1, u2, ediff_l, ediff_flf, need_dwell, literal);
+static __device__ __noinline__ Decision decide_mj_s(double p_r, double u0, double u1, double u2, RaceDraws rd,
+                                                    double ediff_l, double ediff_flf, bool need_dwell) {
+    return decide_mj_screened(p_r, u0, u1, u2, rd, ediff_l, ediff_flf, need_dwell);
 }
-static __device__ __noinline__ Decision decide_ct_s(double p_r, double u0, double u1, double u2, double ediff_fl,
-                                                    bool need_dwell, bool literal) {
-    return decide_ct_screened(p_r, u0, u1, u2, ediff_fl, need_dwell, literal);
+static __device__ __noinline__ Decision decide_ct_s(double p_r, double u0, double u1, double u2, RaceDraws rd,
+                                                    double ediff_fl, bool need_dwell) {
+    return decide_ct_screened(p_r, u0, u1, u2, rd, ediff_fl, need_dwell);
 }
 static __device__ __noinline__ unsigned int decide_discrete_s(double p_flip, double u0, double u1, double ediff,
                                                               bool coin_fired) {

@@ -40,6 +40,7 @@ __device__ __forceinline__ double exp_poly(double x) {
     const double k = t - magic;
     double r = fma(k, kExpC[1], x);
     r = fma(k, kExpC[2], r);
+#ifndef MJ_EXP_ESTRIN
     double s = kExpC[14];
     s = fma(s, r, kExpC[13]);
     s = fma(s, r, kExpC[12]);
@@ -52,6 +53,16 @@ __device__ __forceinline__ double exp_poly(double x) {
     s = fma(s, r, kExpC[5]);
     s = fma(s, r, kExpC[4]);
     s = fma(s, r, kExpC[3]);
+#else
+    // Estrin form of the same polynomial: 1 + (r + r^2 T(r)), T of degree 9 in pairs -- dependency depth 6 instead of
+    // 11 (the exp is the critical path of a Funnel leapfrog step), three multiplications more; 0.7 ulp
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double p0 = fma(kExpC[6], r, kExpC[5]), p1 = fma(kExpC[8], r, kExpC[7]), p2 = fma(kExpC[10], r, kExpC[9]);
+    const double p3 = fma(kExpC[12], r, kExpC[11]), p4 = fma(kExpC[14], r, kExpC[13]);
+    const double q0 = fma(p1, r2, p0), q1 = fma(p3, r2, p2);
+    double s = fma(p4, r8, fma(q1, r4, q0));
+    s = 1.0 + fma(s, r2, r);
+#endif
     double res = __hiloint2double(__double2hiint(s) + (__double2loint(t) << 20), __double2loint(s));
     if (!(fabs(x) < 700.0)) res = exp_out_of_range(x);
     return res;
@@ -125,6 +136,37 @@ __device__ __forceinline__ double cos_halfturns(double u) {
     q = fma(q, z, -4.93480220054467633e+00);
     q = fma(q, z, 1.0);
     return __hiloint2double(__double2hiint(q) ^ sign, __double2loint(q));
+}
+// scale * sin(pi u) and cos(pi u) of the same argument: one range reduction for both (the RoughWell energy is asked
+// for where a gradient has just been evaluated -- both ends of a trajectory).  Operation for operation the two
+// functions above, so the values are bitwise theirs.
+__device__ __forceinline__ double scaled_sincos_halfturns(double u, const double* __restrict__ c, double& cosv) {
+    const double magic = 6755399441055744.0;
+    const double y = u + magic;
+    const double f = u - (y - magic);
+    const int sign = __double2loint(y) << 31;
+    const double fs = __hiloint2double(__double2hiint(f) ^ sign, __double2loint(f));
+    const double z = f * f;
+    double q = c[8];
+    q = fma(q, z, c[7]);
+    q = fma(q, z, c[6]);
+    q = fma(q, z, c[5]);
+    q = fma(q, z, c[4]);
+    q = fma(q, z, c[3]);
+    q = fma(q, z, c[2]);
+    q = fma(q, z, c[1]);
+    q = fma(q, z, c[0]);
+    double r = 4.14956435394258569e-06;
+    r = fma(r, z, -1.04566553387487379e-04);
+    r = fma(r, z, 1.92955627248171321e-03);
+    r = fma(r, z, -2.58068887370022024e-02);
+    r = fma(r, z, 2.35330630129532842e-01);
+    r = fma(r, z, -1.33526276884344708e+00);
+    r = fma(r, z, 4.05871212641649670e+00);
+    r = fma(r, z, -4.93480220054467633e+00);
+    r = fma(r, z, 1.0);
+    cosv = __hiloint2double(__double2hiint(r) ^ sign, __double2loint(r));
+    return q * fs;
 }
 template <typename T> __device__ __forceinline__ T rw_cos_halfturns(T u);
 template <> __device__ __forceinline__ double rw_cos_halfturns<double>(double u) {
@@ -214,6 +256,26 @@ struct RoughWellD {
             if (k < d) s += x[k] * x[k] * inv_2s1sq + rw_cos_halfturns<T>(x[k] * c_pi);
         return s;
     }
+#ifndef MJ_LIB_COSPI
+    // gradient and energy at the same point (grad_aux / energy_after below): the auxiliary value IS the energy
+    static constexpr bool kGradAux = sizeof(T) == 8;
+    __device__ __forceinline__ T grad_aux(const T (&x)[D], T (&g)[D]) const {
+        if constexpr (sizeof(T) == 8) {
+            T s = (T)0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                double cv;
+                g[k] = x[k] * inv_s1sq + scaled_sincos_halfturns(x[k] * c_pi, sc, cv);
+                if (k < d) s += x[k] * x[k] * inv_2s1sq + cv;
+            }
+            return s;
+        } else {
+            grad(x, g);
+            return (T)0;
+        }
+    }
+    __device__ __forceinline__ T energy_with(const T (&x)[D], T e) const { return e; }
+#endif
 };
 
 // LITERAL = false: Neal's funnel  E = x0^2/(2 s^2) + exp(-x0)/2 sum_k xk^2 + (d-1) x0/2
@@ -230,10 +292,11 @@ struct FunnelD {
         for (int k = 1; k < D; ++k) s += x[k] * x[k];
         return s;
     }
-    // grad returns exp(-x0): the energy at the end of a trajectory is asked for at the point of the last gradient
+    // grad_aux returns exp(-x0): the energy at the end of a trajectory is asked for at the point of the last gradient
     // (grad_aux / energy_after below), one exp per trajectory fewer
     static constexpr bool kGradAux = true;
-    __device__ __forceinline__ T grad(const T (&x)[D], T (&g)[D]) const {
+    __device__ __forceinline__ void grad(const T (&x)[D], T (&g)[D]) const { grad_aux(x, g); }
+    __device__ __forceinline__ T grad_aux(const T (&x)[D], T (&g)[D]) const {
         const T e = t_exp<T>(-x[0]);
         const T s = sumsq(x);
         if (LITERAL) {
@@ -281,13 +344,13 @@ struct MultimodalD {
     }
 };
 
-// Energies that share a transcendental with their gradient (Dist::kGradAux): grad returns it, energy_with takes it.
+// Energies that share work with their gradient (Dist::kGradAux): grad_aux returns it, energy_with takes it.
 template <class Dist, class = void> struct grad_has_aux { static constexpr bool value = false; };
-template <class Dist> struct grad_has_aux<Dist, decltype((void)Dist::kGradAux)> { static constexpr bool value = true; };
+template <class Dist> struct grad_has_aux<Dist, decltype((void)Dist::kGradAux)> { static constexpr bool value = Dist::kGradAux; };
 
 template <class Dist, typename T, int D>
 __device__ __forceinline__ T grad_aux(const Dist& dist, const T (&x)[D], T (&g)[D]) {
-    if constexpr (grad_has_aux<Dist>::value) { return dist.grad(x, g); }
+    if constexpr (grad_has_aux<Dist>::value) { return dist.grad_aux(x, g); }
     else { dist.grad(x, g); return (T)0; }
 }
 // energy at the point where the gradient that returned `aux` was evaluated

@@ -157,8 +157,8 @@ fused_sample_kernel(const __grid_constant__ LaunchParams p) {
             v[k] = (live && k < d) ? Vin[(long long)k * p.ld + i] : (T)0;
         }
     }
-    dist.grad(x, g);
-    T EX = dist.energy(x);
+    const T aux0 = grad_aux<Dist, T, D>(dist, x, g);
+    T EX = energy_after<Dist, T, D>(dist, x, aux0);
     T EV = kinetic<T, D>(v);
 
     unsigned int cflags = 0;
@@ -314,11 +314,231 @@ fused_sample_kernel(const __grid_constant__ LaunchParams p) {
     flush_counters(p.counters, loc, (unsigned long long)L);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Same sampler with the particle state kept in SHARED memory between trajectories (ndims >= 6).
+//
+// In fused_sample_kernel a thread holds the state (x, v, g) AND the proposal (xt, vt, gt) in registers: 6 D values,
+// 120 registers at D = 10 in fp64, 168 in all -- three CTAs (12 warps) per SM, and the Funnel of BASELINE config 5 sat
+// on fixed-latency dependency stalls with 45 % of the issue slots used (profiles/r2_fused_funnel10d_cthmc_v2_*.txt).
+// Here the registers hold one trajectory only; the state lives in this thread's own column of a [3][D][128] shared
+// array (conflict-free: lane = column), is loaded when a trajectory starts (30 LDS against ~900 instructions of
+// trajectory) and written back when the proposal is taken.  Same arithmetic in the same order: results are
+// bit-identical to the register kernel (tests/test_gpu_screen.py compares the two).
+template <typename T, int D>
+__host__ __device__ constexpr bool fused_stash() {
+#ifdef MJ_NO_STASH
+    return false;
+#else
+    return sizeof(T) == 8 && D >= 10;
+#endif
+}
+// Measured on the Funnel 10-d point (4M particles, ContinuousTimeHMC, profiles/r2_variants_funnel_stash.txt): the
+// register allocation, not the warp count, is what the shared-memory state buys.  With the register budget of
+// fused_sample_kernel (168, three CTAs) the trajectory no longer shares registers with a second copy of the state
+// and runs 7 % faster; asking for four, five or six CTAs (128 / 96 / 80 registers) spills the trajectory itself and
+// gives +2 %, +0 %, -25 %.  (One warp with four independent DFMA chains already saturates the fp64 pipe of its SM
+// sub-partition -- tools/probe/fp64_probe.cu: latency 8.3 cycles, one warp-DFMA per 2 cycles -- so occupancy is not
+// what this kernel lacks.)
+template <typename T, int D>
+__host__ __device__ constexpr int stash_min_blocks() {
+#ifdef MJ_STASH_MINBLOCKS
+    return MJ_STASH_MINBLOCKS;
+#else
+    return fused_min_blocks<T, D>();
+#endif
+}
+template <typename T, int D>
+constexpr size_t stash_smem_bytes() { return (size_t)4 * D * kFusedThreads * sizeof(T); }     // x, v, g, z
+
+template <class Dist, typename T, int D>
+__global__ void __launch_bounds__(kFusedThreads, stash_min_blocks<T, D>())
+fused_stash_kernel(const __grid_constant__ LaunchParams p) {
+    extern __shared__ __align__(16) unsigned char stash_raw[];
+    typedef T (*Rows)[kFusedThreads];
+    const Rows s_x = (Rows)stash_raw, s_v = s_x + D, s_g = s_v + D, s_z = s_g + D;
+    __shared__ int s_coin[2];
+
+    const int t = threadIdx.x;
+    const long long i = (long long)blockIdx.x * blockDim.x + t;
+    const bool live = i < p.n;
+    const Dist dist(p);
+    const int d = p.d;
+    const T eps = (T)p.eps;
+    const T neg_half_eps = (T)(-p.eps / 2.0);
+    const int L = p.L;
+    const int sampler = p.sampler;
+
+    unsigned int n_l = 0, n_f = 0, n_fl = 0, n_r = 0, n_E = 0, n_exec = 0;
+
+    T xt[D], vt[D], gt[D];                 // the trajectory being integrated; between trajectories: scratch
+    {
+        const T* Xin = (const T*)p.Xin;
+        const T* Vin = (const T*)p.Vin;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            xt[k] = (live && k < d) ? Xin[(long long)k * p.ld + i] : (T)0;
+            vt[k] = (live && k < d) ? Vin[(long long)k * p.ld + i] : (T)0;
+        }
+    }
+    const T aux0 = grad_aux<Dist, T, D>(dist, xt, gt);
+    T EX = energy_after<Dist, T, D>(dist, xt, aux0);
+    T EV = kinetic<T, D>(vt);
+#pragma unroll
+    for (int k = 0; k < D; ++k) { s_x[k][t] = xt[k]; s_v[k][t] = vt[k]; s_g[k][t] = gt[k]; }
+
+    unsigned int cflags = 0;
+    T Hc = (T)0;
+    if (live && sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
+        cflags = p.ca_in[i];
+        Hc = ((const T*)p.Hc_in)[i];
+    }
+    double dwell = 0.0;
+    bool failed = false;
+
+    for (int it = 0; it < p.n_iter; ++it) {
+        const unsigned long long attempt = p.attempt0 + (unsigned long long)it;
+        const bool active = live && !failed;
+        // what the decision does to the state: take the proposal, flip the sign of the momentum it ends with
+        // (F L z = (x', -v'), F z = (x, -v)), refresh the momentum
+        bool moved = false, negate = false, need_r = false;
+        unsigned int choice = 0;
+        const bool need_dwell = p.dwell != nullptr || (it + 1 == p.n_iter && p.dwell_last != nullptr);
+        const T H = EX + EV;                                   // hmc_state.py:80-84
+        T EXl = (T)0, EVl = (T)0;
+        T Hflf = Hc;
+        if (sampler == MJHMC_SAMPLER_DISCRETE) {
+            if (t == 0) s_coin[it & 1] = draw_coin(p, attempt) < p.p_r;   // :138
+            __syncthreads();
+        }
+
+        if (active) {
+            // ---- FLF state (hmc_state.py:109-119): only its energy is ever read
+            if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
+                if (!(cflags & kCacheRef)) n_E += 1;           // the reference evaluates it here
+                if (!(cflags & kCacheValid)) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) { xt[k] = s_x[k][t]; vt[k] = -s_v[k][t]; gt[k] = s_g[k][t]; }
+                    const T aux = leapfrog_L<Dist, T, D>(dist, xt, vt, gt, eps, neg_half_eps, L);
+                    const T EVf = kinetic<T, D>(vt);
+                    const T EXf = energy_after<Dist, T, D>(dist, xt, aux);
+                    Hflf = EXf + EVf;
+                    n_exec += 1;
+                }
+            }
+            // ---- L state (hmc_state.py:93-100)
+#pragma unroll
+            for (int k = 0; k < D; ++k) { xt[k] = s_x[k][t]; vt[k] = s_v[k][t]; gt[k] = s_g[k][t]; }
+            const T auxl = leapfrog_L<Dist, T, D>(dist, xt, vt, gt, eps, neg_half_eps, L);
+            EVl = kinetic<T, D>(vt);
+            EXl = energy_after<Dist, T, D>(dist, xt, auxl);
+            const T Hl = EXl + EVl;
+            n_E += 1;
+            n_exec += 1;
+
+            if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
+                const Decision dc = decide_mj(p, i, attempt, (double)(H - Hl), (double)(H - Hflf), need_dwell);
+                if (dc.fail) { report_failure(p, it); failed = true; }
+                else {
+                    choice = dc.choice; dwell = dc.dwell;
+                    if (choice == 0) { moved = true; Hc = H; cflags = kCacheRef | kCacheValid; n_l += 1; }   // :399
+                    else if (choice == 1) { negate = true; Hc = Hl; cflags = kCacheValid; n_f += 1; }        // :410
+                    else { need_r = true; cflags = 0; n_r += 1; }                                            // :409
+                }
+            } else if (sampler == MJHMC_SAMPLER_CONTINUOUS_TIME) {
+                const Decision dc = decide_ct(p, i, attempt, (double)(H - Hl), need_dwell);                  // F L z :258
+                if (dc.fail) { report_failure(p, it); failed = true; }
+                else {
+                    choice = dc.choice; dwell = dc.dwell;
+                    if (choice == 1) { moved = true; negate = true; n_fl += 1; }
+                    else if (choice == 0) { negate = true; n_f += 1; }
+                    else { need_r = true; n_r += 1; }
+                }
+            } else {
+                const Decision dc = decide_discrete(p, i, attempt, (double)(H - Hl), s_coin[it & 1] != 0);
+                choice = dc.choice;
+                const bool acc = choice & 1u, flip = choice & 2u;
+                moved = acc; negate = acc != flip;                  // F L z, then the flip
+                if (choice & 4u) { need_r = true; n_r += 1; }       // one coin for the whole batch :138
+                n_l += (acc && flip);
+                n_f += (flip && !acc);
+                n_fl += (acc && !flip);
+            }
+
+            // ---- the new state: (xt, vt) become the current position and momentum
+            if (moved) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) { s_x[k][t] = xt[k]; s_g[k][t] = gt[k]; }
+                EX = EXl; EV = EVl;
+            } else {
+#pragma unroll
+                for (int k = 0; k < D; ++k) { xt[k] = s_x[k][t]; vt[k] = s_v[k][t]; }
+            }
+            if (negate) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) vt[k] = -vt[k];
+            }
+        }
+        // ---- R moves: V = V sqrt(1 - beta) + randn sqrt(beta) (hmc_state.py:126), shared by the warp
+        refresh_momentum<T, D>(p, i, attempt, d, need_r, vt, s_z);
+        if (need_r) EV = kinetic<T, D>(vt);
+        if (moved || negate || need_r) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) s_v[k][t] = vt[k];
+        }
+        if (active && !failed) {
+            // ---- record (markov_jump_hmc.py:169,334)
+            if (p.samples) {
+                T* S = (T*)p.samples + (long long)it * p.s_stride_it + i;
+#pragma unroll
+                for (int k = 0; k < D; ++k)
+                    if (k < d) S[(long long)k * p.s_stride_k] = xt[k];
+            }
+            if (p.dwell) p.dwell[(long long)it * p.n + i] = dwell;
+            if (p.choice) p.choice[(long long)it * p.n + i] = (uint8_t)choice;
+            if (p.energy) p.energy[(long long)it * p.n + i] = (double)(EX + EV);      // state.H() after the iteration
+        }
+    }
+
+    if (live) {
+        T* Xout = (T*)p.Xout;
+        T* Vout = (T*)p.Vout;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            if (k < d) {
+                Xout[(long long)k * p.ld + i] = s_x[k][t];
+                Vout[(long long)k * p.ld + i] = s_v[k][t];
+            }
+        }
+        if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
+            p.ca_out[i] = (uint8_t)cflags;
+            ((T*)p.Hc_out)[i] = Hc;
+        }
+        if (p.dwell_last && sampler != MJHMC_SAMPLER_DISCRETE) p.dwell_last[i] = dwell;
+    }
+
+    const unsigned int loc[6] = {n_l, n_f, n_fl, n_r, n_E, n_exec};
+    flush_counters(p.counters, loc, (unsigned long long)L);
+}
+
 // Host-side launcher for one (Dist, T, D) instantiation.
 template <class Dist, typename T, int D>
 cudaError_t launch_fused(const LaunchParams& p, cudaStream_t stream) {
     const long long blocks = (p.n + kFusedThreads - 1) / kFusedThreads;
     if (blocks == 0) return cudaSuccess;
+    if constexpr (fused_stash<T, D>()) {
+        if (!(p.rng_flags & MJHMC_RNG_FLAG_REGISTER_STATE)) {
+            static bool configured = false;
+            if (!configured) {
+                const cudaError_t e = cudaFuncSetAttribute(fused_stash_kernel<Dist, T, D>,
+                                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                           (int)stash_smem_bytes<T, D>());
+                if (e != cudaSuccess) return e;
+                configured = true;
+            }
+            fused_stash_kernel<Dist, T, D><<<(unsigned)blocks, kFusedThreads, stash_smem_bytes<T, D>(), stream>>>(p);
+            return cudaGetLastError();
+        }
+    }
     fused_sample_kernel<Dist, T, D><<<(unsigned)blocks, kFusedThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }

@@ -133,10 +133,13 @@ __device__ __forceinline__ Dist make_stream_dist(const LaunchParams& p, int k0, 
 }
 
 // One trajectory of L leapfrog steps (hmc_state.py:93-100) on this thread's dims; returns the partial energies.
+// want_e0: also the potential energy at the starting point (first iteration of a launch), evaluated together with
+// the first gradient where the energy shares work with it (dists.cuh: grad_aux).
 template <class Dist, typename T, int DT>
 __device__ __forceinline__ void stream_trajectory(const Dist& dist, T (&x)[DT], T (&v)[DT], T eps, T neg_half_eps,
-                                                  int L, T& e_pot, T& e_kin) {
+                                                  int L, T& e_pot, T& e_kin, bool want_e0, T& e0) {
     if constexpr (Dist::kLinear) {
+        if (want_e0) e0 = dist.energy(x);
         if (L > 0) {
 #pragma unroll
             for (int k = 0; k < DT; ++k) v[k] += ((T)0.5 * dist.cf(k)) * x[k];
@@ -151,13 +154,19 @@ __device__ __forceinline__ void stream_trajectory(const Dist& dist, T (&x)[DT], 
 #pragma unroll
             for (int k = 0; k < DT; ++k) v[k] += ((T)0.5 * dist.cf(k)) * x[k];
         }
+        e_pot = dist.energy(x);
     } else {
         T g[DT];
-        dist.grad(x, g);
-        leapfrog_L<Dist, T, DT>(dist, x, v, g, eps, neg_half_eps, L);
+        if (want_e0) {
+            const T aux0 = grad_aux<Dist, T, DT>(dist, x, g);
+            e0 = energy_after<Dist, T, DT>(dist, x, aux0);
+        } else {
+            dist.grad(x, g);
+        }
+        const T aux = leapfrog_L<Dist, T, DT>(dist, x, v, g, eps, neg_half_eps, L);
+        e_pot = energy_after<Dist, T, DT>(dist, x, aux);
     }
     e_kin = kinetic<T, DT>(v);
-    e_pot = dist.energy(x);
 }
 
 template <class Dist, typename T, int DT, int SAMPLER, int LOGG>
@@ -298,10 +307,12 @@ stream_sample_kernel(const __grid_constant__ LaunchParams p, const __grid_consta
             // the draws of this attempt do not depend on the trajectory: the Philox rounds run on the integer pipe
             // before the energies are known
             double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+            RaceDraws rd = {};
             if (decider && active) {
                 const bool need_u2 = !DISCRETE && p.p_r != 0.0;
                 const Uniform3 u = draw_uniforms(p, i, attempt, need_u2);
                 u0 = u.u0; u1 = u.u1; u2 = u.u2;
+                if (!DISCRETE) rd = race_draws(p.p_r, u0, u1, u2, literal_race);
             }
             const bool need_dwell = !DISCRETE && (p.dwell != nullptr || (last && p.dwell_last != nullptr));
 
@@ -309,17 +320,19 @@ stream_sample_kernel(const __grid_constant__ LaunchParams p, const __grid_consta
             if (active) {
 #pragma unroll
                 for (int j = 0; j < DT; ++j) { xt[j] = bx[j * P]; vt[j] = bv[j * P]; }
-                if (it == 0) { ex = dist.energy(xt); ev = kinetic<T, DT>(vt); }
+                if (it == 0) ev = kinetic<T, DT>(vt);
+                T e0 = (T)0;
                 // ---- FLF state (hmc_state.py:109-119): only its energy is ever read
                 if (MJ && !(cflags & kCacheValid)) {
 #pragma unroll
                     for (int j = 0; j < DT; ++j) vt[j] = -vt[j];
-                    stream_trajectory<Dist, T, DT>(dist, xt, vt, eps, neg_half_eps, L, exf, evf);
+                    stream_trajectory<Dist, T, DT>(dist, xt, vt, eps, neg_half_eps, L, exf, evf, false, e0);
 #pragma unroll
                     for (int j = 0; j < DT; ++j) { xt[j] = bx[j * P]; vt[j] = bv[j * P]; }
                 }
-                // ---- L state (hmc_state.py:93-100)
-                stream_trajectory<Dist, T, DT>(dist, xt, vt, eps, neg_half_eps, L, exl, evl);
+                // ---- L state (hmc_state.py:93-100); the energy of the starting point with its first gradient
+                stream_trajectory<Dist, T, DT>(dist, xt, vt, eps, neg_half_eps, L, exl, evl, it == 0, e0);
+                if (it == 0) ex = e0;
             }
 
             // ---- the partial energies of the G threads of a particle meet here
@@ -350,7 +363,7 @@ stream_sample_kernel(const __grid_constant__ LaunchParams p, const __grid_consta
                     T Hflf = Hc;
                     if (!(cflags & kCacheRef)) n_E += 1;           // the reference evaluates the FLF state here
                     if (!(cflags & kCacheValid)) { Hflf = Hf; n_exec += 1; }
-                    const Decision dc = decide_mj_s(p.p_r, u0, u1, u2, (double)(H - Hl), (double)(H - Hflf), need_dwell, literal_race);
+                    const Decision dc = decide_mj_s(p.p_r, u0, u1, u2, rd, (double)(H - Hl), (double)(H - Hflf), need_dwell);
                     if (dc.fail) { report_failure(p, it); failed = true; }
                     else {
                         choice = dc.choice; dwell = dc.dwell;
@@ -359,7 +372,7 @@ stream_sample_kernel(const __grid_constant__ LaunchParams p, const __grid_consta
                         else { cflags = 0; n_r += 1; }                                                // :409
                     }
                 } else if (CT) {
-                    const Decision dc = decide_ct_s(p.p_r, u0, u1, u2, (double)(H - Hl), need_dwell, literal_race);
+                    const Decision dc = decide_ct_s(p.p_r, u0, u1, u2, rd, (double)(H - Hl), need_dwell);
                     if (dc.fail) { report_failure(p, it); failed = true; }
                     else {
                         choice = dc.choice; dwell = dc.dwell;

@@ -23,6 +23,7 @@ B200-specific keyword arguments (all optional, accepted by every class):
     V                initial momentum (default np.random.randn like hmc_state.py:26)
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -41,7 +42,7 @@ INFINITE_RATE_MSG = ("Infinite rate. This occurs when calculating transition rat
                      "Try decreasing the leapfrog stepsize/number of steps or dividing "
                      " the energy by a large constant.")
 
-_B200_KWARGS = ("dtype", "seed", "device", "injected_draws", "particle_offset", "V", "kernel", "sharded", "literal_race")
+_B200_KWARGS = ("dtype", "seed", "device", "injected_draws", "particle_offset", "V", "kernel", "sharded", "literal_race", "register_state")
 
 
 class _CallableEnergy(Distribution):
@@ -90,6 +91,8 @@ class _Engine(object):
         # B200 extension (testing aid): evaluate the three holding times of every attempt literally in fp64 instead of
         # screening the race in single precision first (include/mjhmc_b200.h MJHMC_RNG_FLAG_LITERAL_RACE)
         self.literal_race = bool(opts.get("literal_race"))
+        # B200 extension (testing aid): the register-resident form of the fused kernel also for ndims >= 6
+        self.register_state = bool(opts.get("register_state")) or os.environ.get("MJHMC_B200_REGISTER_STATE") == "1"
         inj = opts.get("injected_draws")
         self.inj = None
         if inj is not None:
@@ -161,7 +164,8 @@ class _Engine(object):
         r.seed = self.seed
         r.attempt0 = int(attempt0)
         r.particle0 = self.offset
-        r.flags = _lib.RNG_FLAG_LITERAL_RACE if self.literal_race else 0
+        r.flags = ((_lib.RNG_FLAG_LITERAL_RACE if self.literal_race else 0)
+                   | (_lib.RNG_FLAG_REGISTER_STATE if self.register_state else 0))
         if self.inj is not None:
             r.mode = _lib.RNG_INJECT
             r.Z = self.inj["Z"].data_ptr() if self.inj["Z"] is not None else None

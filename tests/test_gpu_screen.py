@@ -278,3 +278,46 @@ def test_runs_are_bit_identical_with_and_without_the_screen(idx, resample):
         np.testing.assert_array_equal(np.asarray(x).view(np.int64), np.asarray(y).view(np.int64), err_msg=name)
     if a[4] is not None:
         np.testing.assert_array_equal(a[4].view(np.int64), b[4].view(np.int64), err_msg=name)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# state in shared memory (fused_stash_kernel, ndims >= 6) against the register-resident kernel
+# ---------------------------------------------------------------------------------------------------------------
+def _stash_case(dist_name, d, dtype, kind, register_state, n=40_000, n_iter=10):
+    from mjhmc_b200.misc import distributions as D
+    from mjhmc_b200.samplers import markov_jump_hmc as S
+    from tests.helpers import pin_init
+    rng = np.random.default_rng(100 + d)
+    np.random.seed(99)
+    if dist_name == "Funnel":
+        x0 = 3.0 * rng.standard_normal((1, n))
+        X0 = np.concatenate((x0, np.exp(x0 / 2.) * rng.standard_normal((d - 1, n))))
+        dist = pin_init(D.Funnel(scale=3.0, ndims=d, nbatch=n), X0)
+        eps, L = 0.1, 7
+    elif dist_name == "RoughWell":
+        dist = pin_init(D.RoughWell(ndims=d, nbatch=n, scale1=5, scale2=2), 5 * rng.standard_normal((d, n)))
+        eps, L = 0.3, 5
+    else:
+        dist = pin_init(D.Gaussian(ndims=d, nbatch=n, log_conditioning=2), rng.standard_normal((d, n)))
+        eps, L = 0.4, 6
+    kw = dict(resample=False) if kind in ("ContinuousTimeHMC", "MarkovJumpHMC") else {}
+    s = getattr(S, kind)(distribution=dist, epsilon=eps, beta=0.3, num_leapfrog_steps=L, seed=3, dtype=dtype,
+                         register_state=register_state, **kw)
+    out = s.sample(n_iter)
+    st = s.state
+    counts = (s.l_count, s.f_count, s.fl_count, s.r_count, dist.E_count, dist.dEdX_count)
+    extra = [np.array(s.dwelling_times)] if kind in ("ContinuousTimeHMC", "MarkovJumpHMC") else []
+    return [np.asarray(out), np.array(st.X), np.array(st.V)] + extra, counts
+
+
+@pytest.mark.parametrize("kind", ["HMCBase", "HMC", "ControlHMC", "ContinuousTimeHMC", "MarkovJumpHMC"])
+@pytest.mark.parametrize("dist_name,d,dtype", [("Funnel", 10, "float64"), ("Funnel", 7, "float64"), ("Gaussian", 6, "float64"),
+                                               ("RoughWell", 8, "float64"), ("Gaussian", 16, "float64"),
+                                               ("RoughWell", 13, "float64"), ("Funnel", 10, "float32"),
+                                               ("Gaussian", 16, "float32")])
+def test_shared_memory_state_kernel_equals_the_register_kernel(dist_name, d, dtype, kind):
+    a, ca = _stash_case(dist_name, d, dtype, kind, False)
+    b, cb = _stash_case(dist_name, d, dtype, kind, True)
+    assert ca == cb
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x.view(np.int64), y.view(np.int64))
