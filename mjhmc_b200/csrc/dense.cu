@@ -106,24 +106,52 @@ dense_sample_kernel(const __grid_constant__ LaunchParams p) {
     sh.Xw = cur + warp * (POT ? 2 : 1) * rows * kCols;
     if (POT) sh.Yw = sh.Xw + rows * kCols;
 
-    // ---- stage the matrices once per CTA (zero padded)
-    if (POT) {
-        const double* W = (const double*)p.a0;      // [d][nb], nb == d
-        const double* nu = (const double*)p.a1;
-        const double* b = (const double*)p.a2;
+    // ---- stage the matrix once per CTA (zero padded): one TMA bulk copy per matrix row (cp.async.bulk, 8 d bytes,
+    // global row r -> shared row r at stride ld) on one mbarrier, issued by the lanes of warp 0; the threads zero the
+    // padding the copies do not touch.  Rows that are not 16-byte multiples (odd ndims) are staged with plain loads.
+    __shared__ __align__(8) uint64_t bar_stage;
+    {
+        const double* Mg = (const double*)p.a0;     // Gaussian: S [d][d].  ProductOfT: W [d][nb], nb == d
+        const bool bulk = (d & 1) == 0 && ((uintptr_t)Mg & 15) == 0;
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bar_stage);
+        if (bulk) {
+            if (threadIdx.x == 0) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(d * d * 8)) : "memory");
+            }
+            __syncthreads();
+            if (warp == 0) {
+                for (int r = lane; r < d; r += 32)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"((uint32_t)__cvta_generic_to_shared(sh.A1 + r * ld)), "l"(Mg + (size_t)r * d),
+                                   "r"((uint32_t)(d * 8)), "r"(bar) : "memory");
+            }
+        }
         for (int idx = threadIdx.x; idx < rows * ld; idx += blockDim.x) {
             const int r = idx / ld, c = idx - r * ld;
-            sh.A1[idx] = (r < d && c < d) ? W[r * d + c] : 0.0;
+            const bool data = r < d && c < d;
+            if (!data) sh.A1[idx] = 0.0;
+            else if (!bulk) sh.A1[idx] = Mg[r * d + c];
         }
-        for (int idx = threadIdx.x; idx < rows; idx += blockDim.x) {
-            sh.nu[idx] = idx < d ? nu[idx] : 1.0;
-            sh.bias[idx] = idx < d ? b[idx] : 0.0;
+        if (POT) {
+            const double* nu = (const double*)p.a1;
+            const double* b = (const double*)p.a2;
+            for (int idx = threadIdx.x; idx < rows; idx += blockDim.x) {
+                sh.nu[idx] = idx < d ? nu[idx] : 1.0;
+                sh.bias[idx] = idx < d ? b[idx] : 0.0;
+            }
         }
-    } else {
-        const double* S = (const double*)p.a0;      // [d][d]
-        for (int idx = threadIdx.x; idx < rows * ld; idx += blockDim.x) {
-            const int r = idx / ld, c = idx - r * ld;
-            sh.A1[idx] = (r < d && c < d) ? S[r * d + c] : 0.0;
+        if (bulk) {
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "DSTAGE_WAIT:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+                "@p bra DSTAGE_DONE;\n"
+                "bra DSTAGE_WAIT;\n"
+                "DSTAGE_DONE:\n"
+                "}\n" ::"r"(bar) : "memory");
         }
     }
     for (int idx = lane; idx < (POT ? 2 : 1) * rows * kCols; idx += 32) sh.Xw[idx] = 0.0;

@@ -76,18 +76,19 @@ template <> __device__ __forceinline__ double t_exp<double>(double x) {
 }
 template <> __device__ __forceinline__ float t_exp<float>(float x) { return expf(x); }
 
-// sin(pi u) for u in half-turns, branch free and table free (the fp64 leapfrog loop of RoughWell is
-// nothing but this function).  k = rint(u) by the magic-number add, f = u - k in [-1/2, 1/2],
+// sin(pi u) for u = x w in half-turns, branch free and table free (the fp64 leapfrog loop of RoughWell is
+// nothing but this function).  The product x w is never rounded: k = rint(u) comes out of fma(x, w, magic) by the
+// magic-number add and f = u - k in [-1/2, 1/2] out of a second FMA (one instruction fewer than rounding u first),
 // sin(pi u) = (-1)^k sin(pi f); the parity of k is the low mantissa bit of (u + magic) and is
 // XOR-ed into the sign of f on the integer pipe.  sin(pi f) = f Q(f^2) with Q fitted at Chebyshev
 // nodes on [0, 1/4] (max relative error 3.9e-17 before rounding in fp64, 6.6e-9 in fp32).
 // `c` holds the Q coefficients pre-multiplied by the caller's scale (host side, api.cu), so the
 // return value is scale * sin(pi u).  Valid for |u| < 2^51 (fp64) / 2^22 (fp32); NaN/Inf -> NaN.
 constexpr int kSinCoefF64 = 9, kSinCoefF32 = 5;
-__device__ __forceinline__ double scaled_sin_halfturns(double u, const double* __restrict__ c) {
+__device__ __forceinline__ double scaled_sin_halfturns(double x, double w, const double* __restrict__ c) {
     const double magic = 6755399441055744.0;          // 1.5 * 2^52
-    const double y = u + magic;
-    const double f = u - (y - magic);
+    const double y = fma(x, w, magic);
+    const double f = fma(x, w, -(y - magic));
     const int sign = __double2loint(y) << 31;
     const double fs = __hiloint2double(__double2hiint(f) ^ sign, __double2loint(f));
     const double z = f * f;
@@ -102,10 +103,10 @@ __device__ __forceinline__ double scaled_sin_halfturns(double u, const double* _
     q = fma(q, z, c[0]);
     return q * fs;
 }
-__device__ __forceinline__ float scaled_sin_halfturns(float u, const float* __restrict__ c) {
+__device__ __forceinline__ float scaled_sin_halfturns(float x, float w, const float* __restrict__ c) {
     const float magic = 12582912.0f;                   // 1.5 * 2^23
-    const float y = u + magic;
-    const float f = u - (y - magic);
+    const float y = fmaf(x, w, magic);
+    const float f = fmaf(x, w, -(y - magic));
     const float fs = __int_as_float(__float_as_int(f) ^ (__float_as_int(y) << 31));
     const float z = f * f;
     float q = c[4];
@@ -120,10 +121,10 @@ __device__ __forceinline__ float scaled_sin_halfturns(float u, const float* __re
 // C interpolated at Chebyshev nodes on [0, 1/4] (max abs error 2.8e-16 against the exact cos(pi u) in fp64 arithmetic).
 // A third of the instructions of cospi(); it is the RoughWell energy (distributions.py:295-299), evaluated once per
 // trajectory.  Valid for |u| < 2^51.
-__device__ __forceinline__ double cos_halfturns(double u) {
+__device__ __forceinline__ double cos_halfturns(double x, double w) {
     const double magic = 6755399441055744.0;          // 1.5 * 2^52
-    const double y = u + magic;
-    const double f = u - (y - magic);
+    const double y = fma(x, w, magic);
+    const double f = fma(x, w, -(y - magic));
     const int sign = __double2loint(y) << 31;
     const double z = f * f;
     double q = 4.14956435394258569e-06;
@@ -140,10 +141,10 @@ __device__ __forceinline__ double cos_halfturns(double u) {
 // scale * sin(pi u) and cos(pi u) of the same argument: one range reduction for both (the RoughWell energy is asked
 // for where a gradient has just been evaluated -- both ends of a trajectory).  Operation for operation the two
 // functions above, so the values are bitwise theirs.
-__device__ __forceinline__ double scaled_sincos_halfturns(double u, const double* __restrict__ c, double& cosv) {
+__device__ __forceinline__ double scaled_sincos_halfturns(double x, double w, const double* __restrict__ c, double& cosv) {
     const double magic = 6755399441055744.0;
-    const double y = u + magic;
-    const double f = u - (y - magic);
+    const double y = fma(x, w, magic);
+    const double f = fma(x, w, -(y - magic));
     const int sign = __double2loint(y) << 31;
     const double fs = __hiloint2double(__double2hiint(f) ^ sign, __double2loint(f));
     const double z = f * f;
@@ -168,15 +169,15 @@ __device__ __forceinline__ double scaled_sincos_halfturns(double u, const double
     cosv = __hiloint2double(__double2hiint(r) ^ sign, __double2loint(r));
     return q * fs;
 }
-template <typename T> __device__ __forceinline__ T rw_cos_halfturns(T u);
-template <> __device__ __forceinline__ double rw_cos_halfturns<double>(double u) {
+template <typename T> __device__ __forceinline__ T rw_cos_halfturns(T x, T w);
+template <> __device__ __forceinline__ double rw_cos_halfturns<double>(double x, double w) {
 #ifdef MJ_LIB_COSPI
-    return cospi(u);
+    return cospi(x * w);
 #else
-    return cos_halfturns(u);
+    return cos_halfturns(x, w);
 #endif
 }
-template <> __device__ __forceinline__ float rw_cos_halfturns<float>(float u) { return cospif(u); }
+template <> __device__ __forceinline__ float rw_cos_halfturns<float>(float x, float w) { return cospif(x * w); }
 
 template <typename T, int D>
 struct TestGaussianD {
@@ -247,13 +248,13 @@ struct RoughWellD {
     __device__ __forceinline__ void grad(const T (&x)[D], T (&g)[D]) const {
         // x/s1^2 - sin(2 pi x / s2) 2 pi / s2, the sine evaluated in half-turns with the factor folded in
 #pragma unroll
-        for (int k = 0; k < D; ++k) g[k] = x[k] * inv_s1sq + scaled_sin_halfturns(x[k] * c_pi, sc);
+        for (int k = 0; k < D; ++k) g[k] = x[k] * inv_s1sq + scaled_sin_halfturns(x[k], c_pi, sc);
     }
     __device__ __forceinline__ T energy(const T (&x)[D]) const {
         T s = (T)0;
 #pragma unroll
         for (int k = 0; k < D; ++k)
-            if (k < d) s += x[k] * x[k] * inv_2s1sq + rw_cos_halfturns<T>(x[k] * c_pi);
+            if (k < d) s += x[k] * x[k] * inv_2s1sq + rw_cos_halfturns<T>(x[k], c_pi);
         return s;
     }
 #ifndef MJ_LIB_COSPI
@@ -265,7 +266,7 @@ struct RoughWellD {
 #pragma unroll
             for (int k = 0; k < D; ++k) {
                 double cv;
-                g[k] = x[k] * inv_s1sq + scaled_sincos_halfturns(x[k] * c_pi, sc, cv);
+                g[k] = x[k] * inv_s1sq + scaled_sincos_halfturns(x[k], c_pi, sc, cv);
                 if (k < d) s += x[k] * x[k] * inv_2s1sq + cv;
             }
             return s;

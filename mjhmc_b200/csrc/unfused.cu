@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kThreads) gradient_kernel(DistParams dp, const
             const T c_pi = (T)(2.0 / dp.p[1]);
             T sc[9];
             for (int j = 0; j < (sizeof(T) == 8 ? 9 : 5); ++j) sc[j] = (T)dp.coef[j];
-            for (int k = 0; k < d; ++k) { const T x = X[k * ld + i]; G[k * ld + i] = x * inv_s1sq + scaled_sin_halfturns(x * c_pi, sc); }
+            for (int k = 0; k < d; ++k) { const T x = X[k * ld + i]; G[k * ld + i] = x * inv_s1sq + scaled_sin_halfturns(x, c_pi, sc); }
         } break;
         case MJHMC_DIST_FUNNEL:
         case MJHMC_DIST_FUNNEL_LITERAL: {

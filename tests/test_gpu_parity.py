@@ -26,16 +26,21 @@ def test_golden_trajectory_per_iteration_fp64(name):
     """One launch per sampling_iteration(); state, energies, dwell times and counters after each."""
     g = helpers.load_inject(name)
     s, dist = helpers.product_from_golden(name, g)
+    energy = helpers.energy_from_golden(g)
     assert s._engine.fused
     for it in range(g["X"].shape[0]):
         s.sampling_iteration()
         st = s.state
         assert helpers.rel_err(st.X, g["X"][it]) < TOL["float64"], (name, it)
         assert helpers.rel_err(st.V, g["V"][it]) < TOL["float64"], (name, it)
-        # energies are sums of O(1) terms that cancel (sum of cosines): their error follows the positions' error
-        # times |dE/dx|, not their own magnitude, so they are held to 1e-10 of the array's RMS
-        assert helpers.rel_err(st.EX[0], g["EX"][it], floor_frac=1.0) < TOL["float64"]
-        assert helpers.rel_err(st.EV[0], g["EV"][it], floor_frac=1.0) < TOL["float64"]
+        # energies are sums of terms that cancel (sum of cosines), so their error does not follow their own magnitude:
+        # positions that agree to TOL per element move E by at most sum_k |dE/dx_k| TOL |x_k| (first order), and that
+        # -- the tolerance of the positions carried through the energy -- is what the energies are held to
+        # (a fixed 1e-10 of the array's RMS sat at 0.9e-10 ... 1.0e-10 on the RoughWell case: rounding noise)
+        e_tol = TOL["float64"] * (np.sum(np.abs(g["X"][it] * energy.dEdX(g["X"][it])), axis=0) + np.abs(g["EX"][it]).ravel())
+        assert np.all(np.abs(st.EX[0] - g["EX"][it].ravel()) <= e_tol), (name, it)
+        v_tol = TOL["float64"] * 2.0 * g["EV"][it].ravel()          # d(v^2/2) = v dv <= 2 EV TOL
+        assert np.all(np.abs(st.EV[0] - g["EV"][it].ravel()) <= v_tol + 1e-300), (name, it)
         assert _counters(s, dist) == list(g["counters"][it]), (name, it)
         if name.startswith(("MarkovJumpHMC", "ContinuousTimeHMC")):
             fin = np.isfinite(g["dwell"][it])
