@@ -125,6 +125,17 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
     for (int j = 0; j < 8; ++j) r[j] = __uint_as_float(u[j]);
 }
 
+__device__ __forceinline__ float lg2_approx(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // shared-memory matrix descriptor, no swizzle (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -195,7 +206,9 @@ __global__ void tc_prep_kernel(const float* __restrict__ Mx, int rows, int cols,
 }
 
 // 17 warps: the fifth warp of one SM sub-partition caps the allocation at 16384 / (5 * 32) = 102 -> 96 registers
-template <bool POT>
+// PC: the padded size P when it is known at compile time (112 = the 100-d benchmarks: every core / chunk bound check
+// and table offset below folds to a constant), 0 = taken from the launch
+template <bool POT, int PC>
 __global__ void __launch_bounds__(kTcThreads, 1)
 dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
@@ -210,7 +223,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     __shared__ int s_nr, s_rlist[kTcRows];            // particles of the tile whose momentum is refreshed (R moves)
 
     const int d = p.d;
-    const int P = ((d + 15) >> 4) << 4;            // padded dims (= experts): N of the MMAs and K in steps of 16
+    const int P = PC ? PC : ((d + 15) >> 4) << 4;  // padded dims (= experts): N of the MMAs and K in steps of 16
     const int ncores = P >> 3;
     const int ksteps = P >> 4;
     const int nchunks = (ksteps + 2) >> 1;         // K chunks of a product: steps [0,1), [1,3), [3,5), [5,7)
@@ -391,12 +404,16 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                                     *reinterpret_cast<float4*>(n2) = t4[(1 * P + kc * 8) >> 2]; *reinterpret_cast<float4*>(n2 + 4) = t4[((1 * P + kc * 8) >> 2) + 1];
                                     *reinterpret_cast<float4*>(bb) = t4[(2 * P + kc * 8) >> 2]; *reinterpret_cast<float4*>(bb + 4) = t4[((2 * P + kc * 8) >> 2) + 1];
                                     if (st == 0 || st == L) {
+                                        // (nu+1)/2 log(1 + (y/nu)^2), distributions.py:431, as log2(1 + t) from the
+                                        // special-function unit (absolute error 2^-22 per term, below the rounding of
+                                        // the fp32 sum over 100 experts); ln 2 is applied to the sum
                                         float e = 0.0f;
 #pragma unroll
                                         for (int j = 0; j < 8; ++j) {
                                             const float yy = y[j] + bb[j];
-                                            e += tab[3 * P + kc * 8 + j] * log1pf(yy * yy * tab[4 * P + kc * 8 + j]);   // :431
+                                            e = fmaf(tab[3 * P + kc * 8 + j], lg2_approx(fmaf(yy * yy, tab[4 * P + kc * 8 + j], 1.0f)), e);
                                         }
+                                        e *= 0.693147180559945309f;
                                         if (st == 0) e_start += e;
                                         if (st == L) e_end += e;
                                     }
@@ -404,7 +421,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) {
                                         const float yy = y[j] + bb[j];
-                                        g[j] = __fdividef(a1[j] * yy, n2[j] + yy * yy);
+                                        g[j] = (a1[j] * yy) * rcp_approx(fmaf(yy, yy, n2[j]));
                                     }
                                     split3_store(g, a_lane + (uint32_t)(kc * 4));
                                 }
@@ -727,7 +744,7 @@ cudaError_t dense_tc_prepare(int kind, const float* Mx, const float* nu, const f
     return cudaGetLastError();
 }
 
-template <bool POT>
+template <bool POT, int PC>
 static cudaError_t launch_tc_T(const LaunchParams& p, cudaStream_t stream) {
     int P, nc;
     tc_shape(p.d, P, nc);
@@ -738,18 +755,22 @@ static cudaError_t launch_tc_T(const LaunchParams& p, cudaStream_t stream) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel<POT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel<POT, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     long long blocks = (p.n + 95) / 96;            // ~one tile of jobs per CTA at the least
     if (blocks > sms) blocks = sms;
     if (blocks < 1) blocks = 1;
-    dense_tc_kernel<POT><<<(unsigned)blocks, kTcThreads, smem, stream>>>(p);
+    dense_tc_kernel<POT, PC><<<(unsigned)blocks, kTcThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_dense_tc(int kind, const LaunchParams& p, cudaStream_t stream) {
     if (!p.ws) return cudaErrorInvalidValue;                   // the pre-tiled matrix (mjhmc_dense_tc_prepare)
-    return kind == MJHMC_DIST_PRODUCT_OF_T ? launch_tc_T<true>(p, stream) : launch_tc_T<false>(p, stream);
+    int P, nc;
+    tc_shape(p.d, P, nc);
+    if (P == kTcMaxP)
+        return kind == MJHMC_DIST_PRODUCT_OF_T ? launch_tc_T<true, kTcMaxP>(p, stream) : launch_tc_T<false, kTcMaxP>(p, stream);
+    return kind == MJHMC_DIST_PRODUCT_OF_T ? launch_tc_T<true, 0>(p, stream) : launch_tc_T<false, 0>(p, stream);
 }
 
 }  // namespace mjhmc
