@@ -550,15 +550,20 @@ def roofline_of(ctx, m, peaks):
                 "kernel": "stream_sample_kernel" if streaming else "fused_sample_kernel",
                 "algorithmic_bytes_per_launch": alg, "launch_ms": launch_ms, "note": note}
     if w["dist"] == "RoughWell" and not streaming and w["L"] > 4:
-        # the pipe that does bound this kernel: fp64 instructions of the leapfrog loop per particle-dimension-step
-        # (3 FMAs for the two half kicks and the drift, 15 for x/s1^2 - c sin(2 pi x / s2): dists.cuh)
+        # the pipe that does bound this kernel: fp64 instructions of the leapfrog loop per particle-dimension-step as
+        # the kernel's SASS has them (15: one FMA each for the merged kick and the drift, 13 for
+        # x/s1^2 - c sin(2 pi x / s2) -- two FMAs + one add of range reduction, f^2, eight polynomial FMAs, q * f, and
+        # the FMA that adds x/s1^2; round 1 counted 18 before the kicks were merged and the reduction went to FMAs)
         clk = m.get("clk")
-        fp64_inst = 18.0 * w["ndims"] * m["grads_all"] / world / (m["ms_max"] * 1e-3)
+        fp64_inst = 15.0 * w["ndims"] * m["grads_all"] / world / (m["ms_max"] * 1e-3)
         fp64_peak = 148 * 64 * ((clk or {}).get("sm_mhz") or 1965.0) * 1e6
         roofline["fp64_pipe"] = {"achieved_inst_per_s": fp64_inst, "peak_inst_per_s": fp64_peak,
                                  "frac": fp64_inst / fp64_peak,
-                                 "note": "algorithmic fp64 instructions of the leapfrog loop only; 64 fp64 lanes per SM at "
-                                         "the sampled SM clock (nominal issue rate: MEASURED_PEAKS.json has no fp64 figure)"}
+                                 "inst_per_dim_step": 15,
+                                 "note": "fp64 instructions of the leapfrog loop only (transition, energies, Philox not "
+                                         "counted); peak = 64 fp64 lanes per SM at the sampled SM clock, the rate "
+                                         "tools/probe/fp64_probe.cu measures on B200 (2.0 warp-DFMA per cycle per SM, "
+                                         "profiles/r2_variants_funnel_stash.txt); ncu pipe-active of the same kernel: 70 %"}
     return roofline
 
 
