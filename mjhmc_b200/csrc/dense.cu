@@ -161,18 +161,7 @@ dense_sample_kernel(const __grid_constant__ LaunchParams p) {
     const int L = p.L, sampler = p.sampler;
     unsigned int n_l = 0, n_f = 0, n_fl = 0, n_r = 0, n_E = 0, n_exec = 0;
 
-    // Persistent warps: groups of 8 consecutive particles are handed out through an atomic work
-    // head (row MJHMC_COUNTER_STRIPES of the counter block), so a warp whose particles needed an
-    // extra FLF trajectory does not hold back the other seven warps of its SM, and the matrix is
-    // staged once per SM for the whole launch.
     unsigned long long* work_head = p.counters + (size_t)MJHMC_COUNTER_STRIPES * MJHMC_N_COUNTERS;
-    long long i0 = 0, ic = 0, ip = 0;
-    bool colv[2] = {false, false};
-    bool plive = false;
-    unsigned int cflags = 0;
-    double Hc = 0.0, dwell = 0.0;
-    bool failed = false;
-
     double v[MT][2], g[MT][2];
 
     // Gradient of the positions in Xw -> g, and (when want_e) their energy as per-lane column-pair
@@ -241,35 +230,49 @@ dense_sample_kernel(const __grid_constant__ LaunchParams p) {
         k0 = col_sum(k0) * 0.5; k1 = col_sum(k1) * 0.5;
     };
 
-    // load (x, sign * v) of this warp's particles from the state arrays
-    auto load_state = [&](const double* X, const double* V, double sign) {
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-            const int r = mt * 8 + ar;
-            double2 x = make_double2(0.0, 0.0);
-            v[mt][0] = 0.0; v[mt][1] = 0.0;
-            if (r < d) {
-                if (colv[0]) { x.x = X[(long long)r * p.ld + ic]; v[mt][0] = sign * V[(long long)r * p.ld + ic]; }
-                if (colv[1]) { x.y = X[(long long)r * p.ld + ic + 1]; v[mt][1] = sign * V[(long long)r * p.ld + ic + 1]; }
-            }
-            *reinterpret_cast<double2*>(sh.Xw + r * kCols + 2 * q) = x;
-        }
-        __syncwarp();
-    };
+    // Persistent warps own RANGES of up to 32 consecutive particles (lane j <-> particle start + j), handed out
+    // through an atomic work head (row MJHMC_COUNTER_STRIPES of the counter block, counted in particles), and the
+    // matrix is staged once per SM for the whole launch.  COLUMNS ARE JOBS: per iteration the range is a list of
+    // trajectories -- first the F.L.F trajectories of only those particles whose cached FLF energy is not valid
+    // (hmc_state.py:109-119), then the L trajectory of every particle -- run eight at a time (the N of the MMA).
+    // Until round 2 a warp owned 8 particles and ran a second pass over all 8 whenever one of them needed the FLF
+    // energy: 1.34 passes per 8 particles for ProductOfT-100d at the searched hyper-parameters where 1.05 are needed.
+    // Columns of an MMA are independent, so the packing cannot change a result.
+    const bool mjs = sampler == MJHMC_SAMPLER_MARKOV_JUMP;
+    const long long n_warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+    unsigned int seen_parts = 0, seen_flf = 0;     // this warp's running FLF fraction picks the next range size
 
     for (;;) {
-        unsigned long long grp = 0;
-        if (lane == 0) grp = atomicAdd(work_head, 1ull);
-        grp = __shfl_sync(0xffffffffu, grp, 0);
-        if ((long long)(grp * kCols) >= p.n) break;
-        i0 = (long long)grp * kCols;                  // first particle of this group
-        ic = i0 + 2 * q;                              // this lane's column pair
-        colv[0] = ic < p.n; colv[1] = ic + 1 < p.n;
-        // per-particle bookkeeping lives in lanes 0..7 (lane c <-> particle i0 + c)
-        ip = i0 + lane;
-        plive = lane < kCols && ip < p.n;
-        cflags = 0; Hc = 0.0; dwell = 0.0; failed = false;
-        if (plive && sampler == MJHMC_SAMPLER_MARKOV_JUMP) { cflags = p.ca_in[ip]; Hc = ((const double*)p.Hc_in)[ip]; }
+        // ---- range size: the expected number of passes per particle, E ceil((P + Binomial(P, f)) / 8) / P, is
+        // smallest at these P (tabulated offline for f = FLF fraction); the last ranges of a launch are short so the
+        // warps finish together
+        int take = 32;
+#ifndef MJ_DENSE_FIXED_RANGE
+        if (mjs && seen_parts >= 64u) {
+            const float f = (float)seen_flf / (float)seen_parts;
+            take = f < 0.01f ? 32 : f < 0.035f ? 31 : f < 0.065f ? 30 : f < 0.10f ? 29 : f < 0.16f ? 28
+                 : f < 0.25f ? 32 : f < 0.40f ? 30 : f < 0.90f ? 31 : 32;
+        }
+#else
+        take = MJ_DENSE_FIXED_RANGE;
+#endif
+        long long start = 0;
+        if (lane == 0) {
+            const long long seen_head = (long long)*(volatile unsigned long long*)work_head;
+            if (p.n - seen_head < n_warps_total * 24) take = 8;
+            start = (long long)atomicAdd(work_head, (unsigned long long)take);
+        }
+        start = __shfl_sync(0xffffffffu, start, 0);
+        take = __shfl_sync(0xffffffffu, take, 0);
+        if (start >= p.n) break;
+        const int np = (int)min((long long)take, p.n - start);
+        // per-particle bookkeeping lives in lane j < np (particle start + j)
+        const long long ip = start + lane;
+        const bool plive = lane < np;
+        unsigned int cflags = 0;
+        double Hc = 0.0, dwell = 0.0;
+        bool failed = false;
+        if (plive && mjs) { cflags = p.ca_in[ip]; Hc = ((const double*)p.Hc_in)[ip]; }
 
         for (int it = 0; it < p.n_iter; ++it) {
             const unsigned long long attempt = p.attempt0 + (unsigned long long)it;
@@ -279,20 +282,55 @@ dense_sample_kernel(const __grid_constant__ LaunchParams p) {
             double* Vo = (double*)p.Vout;
             const bool active = plive && !failed;
 
-            // ---- trajectories: pass 0 = FLF energy where the cache does not hold it
-            //      (hmc_state.py:109-119), pass 1 = current energy + the L proposal (hmc_state.py:93-100)
-            double Hflf = Hc, H = 0.0, Hl = 0.0;
-            bool need = false;
-            int first_pass = 1;
-            if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
-                need = active && !(cflags & 2u);
-                if (active && !(cflags & 1u)) n_E += 1;                 // the reference evaluates it here
-                if (__any_sync(0xffffffffu, need)) first_pass = 0;
+            // ---- the job list of this iteration: slots [0, nF) = FLF jobs in particle order, [nF, nF + np) = L jobs
+            const bool need = mjs && active && !(cflags & 2u);
+            const unsigned int needmask = __ballot_sync(0xffffffffu, need);
+            const int nF = __popc(needmask);
+            const int njobs = nF + np;
+            const int sF = __popc(needmask & ((1u << lane) - 1u));          // my FLF slot (if need)
+            const int sL = nF + lane;                                       // my L slot
+            if (active) { n_E += 1; n_exec += 1; }
+            if (mjs && active && !(cflags & 1u)) n_E += 1;                  // the reference evaluates the FLF state here
+            if (need) n_exec += 1;
+            seen_parts += (unsigned int)np; seen_flf += (unsigned int)nF;
+
+            unsigned int coin = 0;
+            if (sampler == MJHMC_SAMPLER_DISCRETE) {
+                if (lane == 0) coin = draw_coin(p, attempt) < p.p_r;
+                coin = __shfl_sync(0xffffffffu, coin, 0);
             }
-            for (int pass = first_pass; pass < 2; ++pass) {
-                load_state(Xc, Vc, pass == 0 ? -1.0 : 1.0);
+
+            double Hflf = Hc, H = 0.0, Hl = 0.0;
+            for (int j0 = 0; j0 < njobs; j0 += kCols) {
+                // ---- this lane's column pair: job slot -> (particle, sign)
+                long long pi[2];
+                int pl[2];                                                  // lane of the particle; -1: empty column
+                double sg[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int slot = j0 + 2 * q + e;
+                    pl[e] = slot >= njobs ? -1 : (slot < nF ? (int)__fns(needmask, 0u, slot + 1) : slot - nF);
+                    sg[e] = slot < nF ? -1.0 : 1.0;
+                    pi[e] = start + (pl[e] < 0 ? 0 : pl[e]);
+                }
+                // ---- load (x, sign * v)
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int r = mt * 8 + ar;
+                    double2 x = make_double2(0.0, 0.0);
+                    v[mt][0] = 0.0; v[mt][1] = 0.0;
+                    if (r < d) {
+                        if (pl[0] >= 0) { x.x = Xc[(long long)r * p.ld + pi[0]]; v[mt][0] = sg[0] * Vc[(long long)r * p.ld + pi[0]]; }
+                        if (pl[1] >= 0) { x.y = Xc[(long long)r * p.ld + pi[1]]; v[mt][1] = sg[1] * Vc[(long long)r * p.ld + pi[1]]; }
+                    }
+                    *reinterpret_cast<double2*>(sh.Xw + r * kCols + 2 * q) = x;
+                }
+                __syncwarp();
+
+                // ---- the trajectory of the 8 columns (hmc_state.py:93-100); st = 0: only dEdX (and E) of the start point
+                double h_start = 0.0, h_end = 0.0;                          // every lane holds column lane & 7
                 double k0, k1, e0, e1;
-                for (int st = 0; st <= L; ++st) {                       // st = 0: only dEdX (and E) of the start point
+                for (int st = 0; st <= L; ++st) {
                     if (st > 0) {
 #pragma unroll
                         for (int mt = 0; mt < MT; ++mt) {
@@ -315,107 +353,103 @@ dense_sample_kernel(const __grid_constant__ LaunchParams p) {
                     if (want_e) {
                         kinetic2(k0, k1);
                         const double h = col_pick(e0 + k0, e1 + k1, lane & 7);      // EX + EV, hmc_state.py:80-84
-                        if (st == 0) { if (pass == 1) H = h; }
-                        if (st == L) { if (pass == 0) { if (need) { Hflf = h; n_exec += 1; } } else Hl = h; }
+                        if (st == 0) h_start = h;
+                        if (st == L) h_end = h;
                     }
                 }
-            }
-            if (active) { n_E += 1; n_exec += 1; }
 
-            // ---- decision per particle (lanes 0..7)
-            unsigned int coin = 0;
-            if (sampler == MJHMC_SAMPLER_DISCRETE) {
-                if (lane == 0) coin = draw_coin(p, attempt) < p.p_r;
-                coin = __shfl_sync(0xffffffffu, coin, 0);
-            }
-            // take: 0 keep, 1 proposal, 2 proposal with flipped momentum; flip / refresh of the resulting momentum
-            unsigned int take = 0, flip = 0, refresh = 0, choice = 0;
-            if (active) {
-                if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) {
-                    const Decision dc = decide_mj(p, ip, attempt, H - Hl, H - Hflf, p.dwell != nullptr || (it + 1 == p.n_iter && p.dwell_last != nullptr));
-                    if (dc.fail) { report_failure(p, it); failed = true; }
-                    else {
-                        choice = dc.choice; dwell = dc.dwell;
-                        if (choice == 0) { take = 1; Hc = H; cflags = 3u; n_l += 1; }
-                        else if (choice == 1) { flip = 1; Hc = Hl; cflags = 2u; n_f += 1; }
-                        else { refresh = 1; cflags = 0u; n_r += 1; }
-                    }
-                } else if (sampler == MJHMC_SAMPLER_CONTINUOUS_TIME) {
-                    const Decision dc = decide_ct(p, ip, attempt, H - Hl, p.dwell != nullptr || (it + 1 == p.n_iter && p.dwell_last != nullptr));
-                    if (dc.fail) { report_failure(p, it); failed = true; }
-                    else {
-                        choice = dc.choice; dwell = dc.dwell;
-                        if (choice == 1) { take = 2; n_fl += 1; }
-                        else if (choice == 0) { flip = 1; n_f += 1; }
-                        else { refresh = 1; n_r += 1; }
-                    }
-                } else {
-                    const Decision dc = decide_discrete(p, ip, attempt, H - Hl, coin != 0);
-                    choice = dc.choice;
-                    const bool acc = choice & 1u, fl = choice & 2u;
-                    if (acc) take = 2;
-                    flip = fl; refresh = (choice & 4u) ? 1u : 0u;
-                    n_l += (acc && fl); n_f += (fl && !acc); n_fl += (acc && !fl); n_r += refresh;
+                // ---- the energies go to the lanes of their particles
+                {
+                    const double hf = __shfl_sync(0xffffffffu, h_end, sF & 7);
+                    if (need && sF >= j0 && sF < j0 + kCols) Hflf = hf;
+                    const double hs = __shfl_sync(0xffffffffu, h_start, sL & 7);
+                    const double hl = __shfl_sync(0xffffffffu, h_end, sL & 7);
+                    if (sL >= j0 && sL < j0 + kCols) { H = hs; Hl = hl; }
                 }
-            }
-            const unsigned int ok = (active && !failed) ? 1u : 0u;
-            const unsigned int code = take | (flip << 2) | (refresh << 3) | (ok << 4);
+                const bool mine = plive && sL >= j0 && sL < j0 + kCols;     // my L job ran in this pass
 
-            // ---- apply to this lane's column pair
-    #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const unsigned int cd = __shfl_sync(0xffffffffu, code, 2 * q + e);
-                const long long i = ic + e;
-                if (!colv[e]) continue;
-                const unsigned int tk = cd & 3u, fp = (cd >> 2) & 1u, rf = (cd >> 3) & 1u, okc = (cd >> 4) & 1u;
-    #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    const int r = mt * 8 + ar;
-                    if (r >= d) continue;
-                    const long long o = (long long)r * p.ld + i;
-                    double xn, vn;
-                    if (okc && tk) {
-                        xn = sh.Xw[r * kCols + 2 * q + e];
-                        vn = tk == 1 ? v[mt][e] : -v[mt][e];
+                // ---- decision per particle whose L job just finished (its FLF job ran in this pass or an earlier one)
+                // take: 0 keep, 1 proposal, 2 proposal with flipped momentum; flip / refresh of the resulting momentum
+                unsigned int tk_ = 0, flip = 0, refresh = 0, choice = 0;
+                if (mine && active) {
+                    if (mjs) {
+                        const Decision dc = decide_mj(p, ip, attempt, H - Hl, H - Hflf, p.dwell != nullptr || (it + 1 == p.n_iter && p.dwell_last != nullptr));
+                        if (dc.fail) { report_failure(p, it); failed = true; }
+                        else {
+                            choice = dc.choice; dwell = dc.dwell;
+                            if (choice == 0) { tk_ = 1; Hc = H; cflags = 3u; n_l += 1; }
+                            else if (choice == 1) { flip = 1; Hc = Hl; cflags = 2u; n_f += 1; }
+                            else { refresh = 1; cflags = 0u; n_r += 1; }
+                        }
+                    } else if (sampler == MJHMC_SAMPLER_CONTINUOUS_TIME) {
+                        const Decision dc = decide_ct(p, ip, attempt, H - Hl, p.dwell != nullptr || (it + 1 == p.n_iter && p.dwell_last != nullptr));
+                        if (dc.fail) { report_failure(p, it); failed = true; }
+                        else {
+                            choice = dc.choice; dwell = dc.dwell;
+                            if (choice == 1) { tk_ = 2; n_fl += 1; }
+                            else if (choice == 0) { flip = 1; n_f += 1; }
+                            else { refresh = 1; n_r += 1; }
+                        }
                     } else {
-                        xn = Xc[o];
-                        vn = Vc[o];
+                        const Decision dc = decide_discrete(p, ip, attempt, H - Hl, coin != 0);
+                        choice = dc.choice;
+                        const bool acc = choice & 1u, fl = choice & 2u;
+                        if (acc) tk_ = 2;
+                        flip = fl; refresh = (choice & 4u) ? 1u : 0u;
+                        n_l += (acc && fl); n_f += (fl && !acc); n_fl += (acc && !fl); n_r += refresh;
                     }
-                    if (okc && fp) vn = -vn;
-                    if (okc && rf) {
-                        double z0, z1;
-                        normal_pair(p, i, attempt, r >> 1, d, z0, z1);
-                        vn = vn * p.r_keep + ((r & 1) ? z1 : z0) * p.r_mix;        // hmc_state.py:126
-                    }
-                    Xo[o] = xn;
-                    Vo[o] = vn;
-                    if (okc && p.samples) ((double*)p.samples)[(long long)r * p.s_stride_k + (long long)it * p.s_stride_it + i] = xn;
                 }
+                const unsigned int ok = (mine && active && !failed) ? 1u : 0u;
+                const unsigned int code = tk_ | (flip << 2) | (refresh << 3) | (ok << 4);
+
+                // ---- apply to the L-job columns of this lane's pair
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const unsigned int cd = __shfl_sync(0xffffffffu, code, pl[e] < 0 ? 0 : pl[e]);
+                    if (pl[e] < 0 || sg[e] < 0.0) continue;                 // empty column / FLF job: only its energy is read
+                    const long long i = pi[e];
+                    const unsigned int tk = cd & 3u, fp = (cd >> 2) & 1u, rf = (cd >> 3) & 1u, okc = (cd >> 4) & 1u;
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const int r = mt * 8 + ar;
+                        if (r >= d) continue;
+                        const long long o = (long long)r * p.ld + i;
+                        double xn, vn;
+                        if (okc && tk) {
+                            xn = sh.Xw[r * kCols + 2 * q + e];
+                            vn = tk == 1 ? v[mt][e] : -v[mt][e];
+                        } else {
+                            xn = Xc[o];
+                            vn = Vc[o];
+                        }
+                        if (okc && fp) vn = -vn;
+                        if (okc && rf) {
+                            double z0, z1;
+                            normal_pair(p, i, attempt, r >> 1, d, z0, z1);
+                            vn = vn * p.r_keep + ((r & 1) ? z1 : z0) * p.r_mix;        // hmc_state.py:126
+                        }
+                        Xo[o] = xn;
+                        Vo[o] = vn;
+                        if (okc && p.samples) ((double*)p.samples)[(long long)r * p.s_stride_k + (long long)it * p.s_stride_it + i] = xn;
+                    }
+                }
+                if (ok) {
+                    if (p.dwell) p.dwell[(long long)it * p.n + ip] = dwell;
+                    if (p.choice) p.choice[(long long)it * p.n + ip] = (uint8_t)choice;
+                }
+                __syncwarp();
             }
-            if (active && !failed) {
-                if (p.dwell) p.dwell[(long long)it * p.n + ip] = dwell;
-                if (p.choice) p.choice[(long long)it * p.n + ip] = (uint8_t)choice;
-            }
-            __syncwarp();
         }
 
         if (plive) {
-            if (sampler == MJHMC_SAMPLER_MARKOV_JUMP) { p.ca_out[ip] = (uint8_t)cflags; ((double*)p.Hc_out)[ip] = Hc; }
+            if (mjs) { p.ca_out[ip] = (uint8_t)cflags; ((double*)p.Hc_out)[ip] = Hc; }
             if (p.dwell_last && sampler != MJHMC_SAMPLER_DISCRETE) p.dwell_last[ip] = dwell;
         }
-        if (p.n_iter == 0) {
+        if (p.n_iter == 0 && plive) {
             // nothing ran: the state still has to reach the output buffers
-            load_state((const double*)p.Xin, (const double*)p.Vin, 1.0);
-    #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                if (!colv[e]) continue;
-    #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    const int r = mt * 8 + ar;
-                    if (r >= d) continue;
-                    ((double*)p.Xout)[(long long)r * p.ld + ic + e] = sh.Xw[r * kCols + 2 * q + e];
-                    ((double*)p.Vout)[(long long)r * p.ld + ic + e] = v[mt][e];
-                }
+            for (int r = 0; r < d; ++r) {
+                ((double*)p.Xout)[(long long)r * p.ld + ip] = ((const double*)p.Xin)[(long long)r * p.ld + ip];
+                ((double*)p.Vout)[(long long)r * p.ld + ip] = ((const double*)p.Vin)[(long long)r * p.ld + ip];
             }
         }
     }

@@ -212,7 +212,7 @@ template <bool POT, int PC>
 __global__ void __launch_bounds__(kTcThreads, 1)
 dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
-    __shared__ __align__(8) uint64_t bar_tma, bar_done, bar_chunk[kTcCPT];
+    __shared__ __align__(8) uint64_t bar_tma, bar_done[kTcCPT], bar_chunk[kTcCPT];
     __shared__ uint32_t s_tmem;
     __shared__ int s_coin;
     __shared__ int s_wsum[4];
@@ -239,9 +239,8 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     // ---- one-time setup: barriers, TMEM, the matrix planes via TMA
     if (tid == 0) {
         mbar_init(&bar_tma, 1);
-        mbar_init(&bar_done, 1);
 #pragma unroll
-        for (int c = 0; c < kTcCPT; ++c) mbar_init(&bar_chunk[c], kTcEpiThreads);
+        for (int c = 0; c < kTcCPT; ++c) { mbar_init(&bar_done[c], 1); mbar_init(&bar_chunk[c], kTcEpiThreads); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(&s_tmem, kTcTmemCols);
@@ -275,6 +274,11 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     const int L = p.L, sampler = p.sampler;
     const bool mj = sampler == MJHMC_SAMPLER_MARKOV_JUMP;
     const int nprod = POT ? 2 * L + 2 : L + 1;     // products of one tile trajectory
+#ifdef TC_NO_NSPLIT
+    constexpr bool kNSplit = false;
+#else
+    constexpr bool kNSplit = PC == kTcMaxP;        // 4 K chunks, the last one two full K steps
+#endif
     unsigned int n_l = 0, n_f = 0, n_fl = 0, n_r = 0, n_E = 0, n_exec = 0;
     uint32_t pc = 0;                               // running product counter: barrier parities, accumulator choice
     // my TMEM window: lane quarter of my warp (warp % 4), accumulator column of core column kc = 8 kc
@@ -387,13 +391,14 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                 for (int st = 0; st <= L; ++st) {
                     if (POT) {
                         // ---- phase 1: Y = X W + b  ->  G (and the energy at the two ends of the trajectory)
-                        mbar_wait(&bar_done, pc & 1u);
-                        TCX_EV(2 * st, 0)
-                        tc_fence_after();
+                        const uint32_t par1 = pc & 1u;
                         ++pc;
 #pragma unroll
                         for (int c = 0; c < kTcCPT; ++c) {
                             if (c < nchunks) {
+                                mbar_wait(&bar_done[c], par1);             // columns of chunk c of Y are complete
+                                TCX_EV(2 * st, 0)
+                                tc_fence_after();
                                 const int kc = tc_core(c, q);
                                 if (kc < ncores) {
                                     float y[8];
@@ -433,11 +438,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                         }
                     }
                     // ---- gradient sweep: kick, drift, next positions
-                    { TCX_T0
-                    mbar_wait(&bar_done, pc & 1u);
-                    TCX_ACC(0) }
-                    TCX_EV(POT ? 2 * st + 1 : st, 0)
-                    tc_fence_after();
+                    const uint32_t par2 = pc & 1u;
                     const uint32_t dcol = tmem_base + my_lane + (POT ? 128u : ((pc & 1u) ? 128u : 0u));
                     ++pc;
                     if (st > 0 && st < L) {
@@ -446,6 +447,11 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
 #pragma unroll
                         for (int c = 0; c < kTcCPT; ++c) {
                             if (c < nchunks) {
+                                { TCX_T0
+                                mbar_wait(&bar_done[c], par2);             // columns of chunk c of the gradient are complete
+                                TCX_ACC(0) }
+                                TCX_EV(POT ? 2 * st + 1 : st, 0)
+                                tc_fence_after();
                                 const int kc = tc_core(c, q);
                                 if (kc < ncores) {
                                     float g[8];
@@ -475,6 +481,8 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
 #pragma unroll
                         for (int c = 0; c < kTcCPT; ++c) {
                             if (c < nchunks) {
+                                mbar_wait(&bar_done[c], par2);
+                                tc_fence_after();
                                 const int kc = tc_core(c, q);
                                 if (kc < ncores) {
                                     float g[8];
@@ -532,7 +540,36 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                         TCX_EV(prod - 1, 5 + c)
                         tc_fence_after();
                         TCX_T0
-                        if (elect_one()) {
+                        if (kNSplit && c == nchunks - 1) {
+                            // Last K chunk: issued per group of accumulator columns (the column ranges of the epilogue's
+                            // chunks: 16, 32, 32, 32) with one commit each, so the epilogue starts on the first columns of
+                            // this product while the tensor core still works on the others.
+                            if (elect_one()) {
+#pragma unroll
+                                for (int nc = 0; nc < kTcCPT; ++nc) {
+                                    const uint32_t n0 = nc ? 32u * nc - 16u : 0u, nw = nc ? 32u : 16u;
+                                    const uint32_t idn = (idesc & ~(0x3Fu << 17)) | ((nw >> 3) << 17);
+                                    // 16-byte units per 8 accumulator columns: one core matrix along a row of cores
+                                    // (MN-major view) or one row of cores (K-major view)
+                                    const uint32_t bn = (n0 >> 3) * (y_prod ? 8u : (uint32_t)ncores * 8u);
+#pragma unroll
+                                    for (int kk = 0; kk < 2; ++kk) {
+                                        const int kg = 2 * c - 1 + kk;
+                                        const uint32_t bo = (uint32_t)kg * bstep + bn;
+                                        const uint32_t a0t = tmem_base + kTcACol + (uint32_t)kg * 8u, a1t = a0t + kTcPlaneCols, a2t = a1t + kTcPlaneCols;
+                                        const uint64_t b0d = bhi | (uint64_t)(b_lo[0] + bo), b1d = bhi | (uint64_t)(b_lo[1] + bo),
+                                                       b2d = bhi | (uint64_t)(b_lo[2] + bo);
+                                        umma_bf16_ts(dacc + n0, a0t, b0d, idn, 1u);
+                                        umma_bf16_ts(dacc + n0, a0t, b1d, idn, 1u);
+                                        umma_bf16_ts(dacc + n0, a1t, b0d, idn, 1u);
+                                        umma_bf16_ts(dacc + n0, a1t, b1d, idn, 1u);
+                                        umma_bf16_ts(dacc + n0, a0t, b2d, idn, 1u);
+                                        umma_bf16_ts(dacc + n0, a2t, b0d, idn, 1u);
+                                    }
+                                    umma_commit(&bar_done[nc]);
+                                }
+                            }
+                        } else if (elect_one()) {
 #pragma unroll
                             for (int kk = 0; kk < 2; ++kk) {
                                 const int kg = 2 * c - 1 + kk;
@@ -551,7 +588,11 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
 #endif
                                 }
                             }
-                            if (c == nchunks - 1) umma_commit(&bar_done);
+                            if (c == nchunks - 1) {
+#pragma unroll
+                                for (int cc = 0; cc < kTcCPT; ++cc)
+                                    if (cc < nchunks) umma_commit(&bar_done[cc]);
+                            }
                         }
                         __syncwarp();
                         TCX_EV(prod - 1, 9 + c)

@@ -641,7 +641,11 @@ class HMCBase(object):
         if not hasattr(eng, "copy_stream"):
             eng.copy_stream = torch.cuda.Stream(device=eng.device)
         main = torch.cuda.current_stream(eng.device)
-        bounds = [n_samples * c // chunks for c in range(chunks + 1)]
+        # the copy engine is the bottleneck (a chunk's copy outlasts the next chunk's kernel), so the only kernel
+        # time it ever waits for is the first chunk's: that chunk is a quarter of the others
+        first = max(1, n_samples // (4 * chunks)) if chunks > 1 else n_samples
+        rest = n_samples - first
+        bounds = [0] + [first + rest * c // max(1, chunks - 1) for c in range(chunks)] if chunks > 1 else [0, n_samples]
         keep = []
         for c in range(chunks):
             c0, c1 = bounds[c], bounds[c + 1]
