@@ -313,17 +313,22 @@ dense_sample_kernel(const __grid_constant__ LaunchParams p) {
                     sg[e] = slot < nF ? -1.0 : 1.0;
                     pi[e] = start + (pl[e] < 0 ? 0 : pl[e]);
                 }
-                // ---- load (x, sign * v)
+                // ---- load (x, sign * v): every load is issued before the first value is used (clamped row, the
+                // first particle of the range for an empty column) -- with a branch per row the loads of one row waited
+                // for the shared-memory store of the row before: 13 DRAM round trips per pass
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const long long ro = (long long)min(mt * 8 + ar, d - 1) * p.ld;
+                    g[mt][0] = Xc[ro + pi[0]]; g[mt][1] = Xc[ro + pi[1]];
+                    v[mt][0] = Vc[ro + pi[0]]; v[mt][1] = Vc[ro + pi[1]];
+                }
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
                     const int r = mt * 8 + ar;
-                    double2 x = make_double2(0.0, 0.0);
-                    v[mt][0] = 0.0; v[mt][1] = 0.0;
-                    if (r < d) {
-                        if (pl[0] >= 0) { x.x = Xc[(long long)r * p.ld + pi[0]]; v[mt][0] = sg[0] * Vc[(long long)r * p.ld + pi[0]]; }
-                        if (pl[1] >= 0) { x.y = Xc[(long long)r * p.ld + pi[1]]; v[mt][1] = sg[1] * Vc[(long long)r * p.ld + pi[1]]; }
-                    }
-                    *reinterpret_cast<double2*>(sh.Xw + r * kCols + 2 * q) = x;
+                    const bool in0 = r < d && pl[0] >= 0, in1 = r < d && pl[1] >= 0;
+                    v[mt][0] = in0 ? sg[0] * v[mt][0] : 0.0;
+                    v[mt][1] = in1 ? sg[1] * v[mt][1] : 0.0;
+                    *reinterpret_cast<double2*>(sh.Xw + r * kCols + 2 * q) = make_double2(in0 ? g[mt][0] : 0.0, in1 ? g[mt][1] : 0.0);
                 }
                 __syncwarp();
 
@@ -402,25 +407,38 @@ dense_sample_kernel(const __grid_constant__ LaunchParams p) {
                 const unsigned int ok = (mine && active && !failed) ? 1u : 0u;
                 const unsigned int code = tk_ | (flip << 2) | (refresh << 3) | (ok << 4);
 
-                // ---- apply to the L-job columns of this lane's pair
+                // ---- apply to the L-job columns of this lane's pair.  A particle that did not take the trajectory keeps
+                // its state: where a column of the warp needs it, the old state of the column is fetched in one batch of
+                // independent loads into the (dead) gradient registers (load -> store pairs row by row serialise on the
+                // memory latency: Xout may alias Xin)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const unsigned int cd = __shfl_sync(0xffffffffu, code, pl[e] < 0 ? 0 : pl[e]);
-                    if (pl[e] < 0 || sg[e] < 0.0) continue;                 // empty column / FLF job: only its energy is read
+                    const bool lcol = pl[e] >= 0 && sg[e] > 0.0;           // not an empty column / an FLF job (only its energy is read)
                     const long long i = pi[e];
                     const unsigned int tk = cd & 3u, fp = (cd >> 2) & 1u, rf = (cd >> 3) & 1u, okc = (cd >> 4) & 1u;
+                    const bool took = okc && tk;
+                    if (__any_sync(0xffffffffu, lcol && !took)) {
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const long long o = (long long)min(mt * 8 + ar, d - 1) * p.ld + i;
+                            g[mt][0] = Xc[o];
+                            g[mt][1] = Vc[o];
+                        }
+                    }
+                    if (!lcol) continue;
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
                         const int r = mt * 8 + ar;
                         if (r >= d) continue;
                         const long long o = (long long)r * p.ld + i;
                         double xn, vn;
-                        if (okc && tk) {
+                        if (took) {
                             xn = sh.Xw[r * kCols + 2 * q + e];
                             vn = tk == 1 ? v[mt][e] : -v[mt][e];
                         } else {
-                            xn = Xc[o];
-                            vn = Vc[o];
+                            xn = g[mt][0];
+                            vn = g[mt][1];
                         }
                         if (okc && fp) vn = -vn;
                         if (okc && rf) {
