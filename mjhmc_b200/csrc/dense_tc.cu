@@ -37,7 +37,10 @@ namespace mjhmc {
 constexpr int kTcRows = 128;                       // job rows per tile (M of the MMA)
 constexpr int kTcSplit = 4;                        // epilogue threads per row
 constexpr int kTcEpiThreads = kTcRows * kTcSplit;  // 16 warps; warp w reads TMEM lanes 32 (w % 4) ..
-constexpr int kTcThreads = kTcEpiThreads + 32;     // + the MMA-issuing warp
+constexpr int kTcHelpers = 96;                     // three helper warps: draws of the tile, momentum refresh of the tile before
+constexpr int kTcThreads = kTcEpiThreads + 32 + kTcHelpers;   // + the MMA-issuing warp + the helpers (20 warps = 5 per
+                                                   // SM sub-partition: the same 96-register cap as 17 warps)
+constexpr int kTcDeferMax = 24;                    // more R movers than this in a tile: every thread refreshes them at once
 constexpr int kTcMaxP = 112;                       // padded dims / experts (K and N of the MMAs), a multiple of 16
 constexpr int kTcCPT = 4;                          // 8-wide core columns per thread (and K chunks per product)
 constexpr int kTcTmemCols = 512;                   // two accumulators of 128 columns + three A planes of 64
@@ -212,7 +215,7 @@ template <bool POT, int PC>
 __global__ void __launch_bounds__(kTcThreads, 1)
 dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
-    __shared__ __align__(8) uint64_t bar_tma, bar_done[kTcCPT], bar_chunk[kTcCPT];
+    __shared__ __align__(8) uint64_t bar_tma, bar_st, bar_done[kTcCPT], bar_chunk[kTcCPT];
     __shared__ uint32_t s_tmem;
     __shared__ int s_coin;
     __shared__ int s_wsum[4];
@@ -220,7 +223,9 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     __shared__ int s_flf_row[kTcRows];                // particle of the chunk -> row of its FLF job, -1 = none
     __shared__ int s_row_part[kTcRows];               // FLF row -> particle of the chunk
     __shared__ unsigned int s_code[kTcRows];          // decision of each particle, broadcast to its 4 threads
-    __shared__ int s_nr, s_rlist[kTcRows];            // particles of the tile whose momentum is refreshed (R moves)
+    __shared__ int s_nr[2], s_rlist[2][kTcRows];      // particles of the tile whose momentum is refreshed (R moves); two tiles
+    __shared__ double s_u[3][kTcRows];                // the uniforms of the tile's particles (drawn by the helper warps)
+    __shared__ RaceDraws s_rd[kTcRows];               // and the uniform-only half of the holding-time race screen
 
     const int d = p.d;
     const int P = PC ? PC : ((d + 15) >> 4) << 4;  // padded dims (= experts): N of the MMAs and K in steps of 16
@@ -231,14 +236,23 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     const uint32_t ws_bytes = 3u * b_plane + (POT ? (uint32_t)(kTcTabs * P * 4) : 0u);
     uint8_t* B0 = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);
     const float* tab = reinterpret_cast<const float*>(B0 + 3u * b_plane);
+    // State stash: the (dims x 128 particles) boxes of X and V the tile starts from, row k at k * 128 floats.  Filled by
+    // one bulk copy (TMA) per row, issued when the tile before has let go of the stash -- beside its stores and this
+    // tile's plan -- read by the job rows (an FLF job shares the columns of its particle's L job) and again by the
+    // particles that do not take their trajectory.
+    float* const stX = reinterpret_cast<float*>(B0 + ((ws_bytes + 127u) & ~127u));
+    float* const stV = stX + P * kTcRows;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool epi = tid < kTcEpiThreads;
+    const bool mma_warp = warp == kTcEpiThreads / 32;
+    const bool literal_race = (p.rng_flags & MJHMC_RNG_FLAG_LITERAL_RACE) != 0;
     const int m = tid & (kTcRows - 1);             // job row of the tile
     const int q = (tid >> 7) & 3;                  // which core columns: q, 4+q, 8+q, 12+q
 
     // ---- one-time setup: barriers, TMEM, the matrix planes via TMA
     if (tid == 0) {
         mbar_init(&bar_tma, 1);
+        mbar_init(&bar_st, 1);
 #pragma unroll
         for (int c = 0; c < kTcCPT; ++c) { mbar_init(&bar_done[c], 1); mbar_init(&bar_chunk[c], kTcEpiThreads); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -286,7 +300,8 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     const uint32_t a_lane = tmem_base + my_lane + kTcACol;       // my row of A plane 0 (core kc = columns 4 kc ..)
 
     // contiguous particle range of this CTA
-    const long long r0 = p.n * (long long)blockIdx.x / gridDim.x, r1 = p.n * (long long)(blockIdx.x + 1) / gridDim.x;
+    const long long r0 = (p.n * (long long)blockIdx.x / gridDim.x) & ~3ll;
+    const long long r1 = blockIdx.x + 1 == gridDim.x ? p.n : (p.n * (long long)(blockIdx.x + 1) / gridDim.x) & ~3ll;
 
     float x[kTcCPT][8], v[kTcCPT][8];
 #ifdef TCX_TRACE
@@ -297,7 +312,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
 #define TCX_EV(prod, slot)
 #endif
 #ifdef TCX_TIMING
-    long long tph[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
+    long long tph[7] = {0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
     long long tw[6] = {0, 0, 0, 0, 0, 0};          // epilogue: [0] wait bar_done, [1] work; MMA warp: [0..3] wait chunk c, [4] issue
 #define TCX_T0 const long long tq0 = clock64();
 #define TCX_ACC(k) tw[k] += clock64() - tq0;
@@ -308,6 +323,44 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
 #define TCX_ACC(k)
 #endif
 
+    // Momentum refresh (hmc_state.py:121-129) of the R movers of one tile: (particle, Box-Muller pair) jobs dealt to
+    // the threads first, first + stride, ...
+    auto refresh_jobs = [&](const int* list, int nr, long long base, unsigned long long att, int first, int stride) {
+        const float rk = (float)p.r_keep, rm = (float)p.r_mix;
+        float* Vo = (float*)p.Vout;
+        const int npairs = (d + 1) >> 1, njobs = nr * npairs;
+        for (int job = first; job < njobs; job += stride) {
+            const int r = job / npairs, pr = job - r * npairs;
+            const long long ip = base + list[r];
+            double z0, z1;
+            normal_pair(p, ip, att, pr, d, z0, z1);
+            const long long o0 = (long long)(2 * pr) * p.ld + ip;
+            Vo[o0] = (rk != 0.0f ? Vo[o0] * rk : 0.0f) + (float)z0 * rm;  // hmc_state.py:126
+            if (2 * pr + 1 < d) {
+                const long long o1 = o0 + p.ld;
+                Vo[o1] = (rk != 0.0f ? Vo[o1] * rk : 0.0f) + (float)z1 * rm;
+            }
+        }
+    };
+    const bool bulk_base_ok = (p.ld & 3) == 0 &&
+        ((((uintptr_t)p.Xin) | ((uintptr_t)p.Vin) | ((uintptr_t)p.Xout) | ((uintptr_t)p.Vout)) & 15u) == 0;
+    // one bulk copy per row of the two boxes (threads 0 .. 2d-1); false: the tile fills the stash with plain loads
+    auto stash_issue = [&](const float* Xs, const float* Vs, long long c0) -> bool {
+        const bool ok = bulk_base_ok && (c0 & 3) == 0 && c0 + kTcRows <= p.n;
+        if (ok && tid < 2 * d) {
+            if (tid == 0) mbar_expect_tx(&bar_st, (uint32_t)(2 * d * kTcRows * 4));
+            const int k = tid < d ? tid : tid - d;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tma_bulk_g2s((tid < d ? stX : stV) + k * kTcRows, (tid < d ? Xs : Vs) + (long long)k * p.ld + c0, kTcRows * 4, &bar_st);
+        }
+        return ok;
+    };
+    uint32_t st_par = 0;                           // parity of the stash fill the next bulk-filled tile waits for
+    bool stash_bulk = false;                       // the coming tile's stash was requested with bulk copies
+    int tb = 0;                                    // tile parity: which s_rlist / s_nr this tile fills
+    int pend_nr = 0, pend_buf = 0;                 // R movers of the tile before, refreshed by the helper warps during this one
+    long long pend_cur = 0;
+
     for (int it = 0; it < p.n_iter; ++it) {
         const unsigned long long attempt = p.attempt0 + (unsigned long long)it;
         const float* Xc = (const float*)(it == 0 ? p.Xin : p.Xout);
@@ -317,6 +370,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
         float* Xo = (float*)p.Xout;
         float* Vo = (float*)p.Vout;
         if (sampler == MJHMC_SAMPLER_DISCRETE && tid == 0) s_coin = draw_coin(p, attempt) < p.p_r;
+        if (r0 < r1) stash_bulk = stash_issue(Xc, Vc, r0);
 
         for (long long cur = r0; cur < r1;) {
             // ---- plan the tile: particles cur .. cur+np-1 with np + #FLF jobs <= 128
@@ -334,13 +388,15 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                 }
                 if (lane == 31) s_wsum[warp] = incl;
             }
-            if (tid == 0) s_nr = 0;
+            if (tid == 0) s_nr[tb] = 0;
             __syncthreads();
             if (tid < kTcRows) {
                 for (int w = 0; w < warp; ++w) incl += s_wsum[w];
                 s_flf_row[tid] = -1;
             }
-            const int np = __syncthreads_count(tid < kTcRows && valid && incl <= kTcRows);
+            int np = __syncthreads_count(tid < kTcRows && valid && incl <= kTcRows);
+            // tiles start at multiples of 4 particles (16-byte aligned rows for the bulk copies of the state stash)
+            if (cur + np < r1) np &= ~3;
             const bool mine = tid < np;                                     // lead thread of an L job
             if (mine && need) {
                 const int row = np + (incl - (tid + 1) - 1);                // FLF rows follow the L rows, in particle order
@@ -359,20 +415,42 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
             const float sign = is_flf ? -1.0f : 1.0f;
             const bool live = is_l || is_flf;
 
+            // ---- the stash holds the boxes of particles cur .. cur + 127
+            if (stash_bulk) {
+                if (epi) mbar_wait(&bar_st, st_par);
+                st_par ^= 1u;
+            } else {
+                // rows that are not 16-byte aligned, or the ragged end of the cloud: plain loads
+                for (int idx = tid; idx < 2 * d * kTcRows; idx += kTcThreads) {
+                    const int a = idx / (d * kTcRows), rem = idx - a * (d * kTcRows);
+                    const int k = rem / kTcRows, mm = rem - k * kTcRows;
+                    const long long gi = cur + mm;
+                    const float val = gi < p.n ? (a ? Vc : Xc)[(long long)k * p.ld + gi] : 0.0f;
+                    (a ? stV : stX)[k * kTcRows + mm] = val;
+                }
+                __syncthreads();
+            }
+
             if (epi) {
-                // ---- load my slice of (x, +-v)
+                // ---- my slice of (x, +-v) from the stash
                 float ev0 = 0.0f;
 #pragma unroll
                 for (int c = 0; c < kTcCPT; ++c) {
                     const int kc = tc_core(c, q);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int k = kc * 8 + j;
-                        x[c][j] = 0.0f; v[c][j] = 0.0f;
-                        if (live && k < d) { x[c][j] = Xc[(long long)k * p.ld + i]; v[c][j] = sign * Vc[(long long)k * p.ld + i]; }
-                        ev0 += v[c][j] * v[c][j];
+                        const bool in = live && kc * 8 + j < d;
+                        x[c][j] = in ? stX[(kc * 8 + j) * kTcRows + part] : 0.0f;
+                        v[c][j] = in ? stV[(kc * 8 + j) * kTcRows + part] : 0.0f;
                     }
                 }
+#pragma unroll
+                for (int c = 0; c < kTcCPT; ++c)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        v[c][j] *= sign;
+                        ev0 += v[c][j] * v[c][j];
+                    }
                 float e_start = 0.0f, e_end = 0.0f;
                 TCX_MARK(1)
 
@@ -522,7 +600,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                     for (int j = 0; j < 8; ++j) ev1 += v[c][j] * v[c][j];       // slots beyond my dims hold 0
                 s_red[0][q][m] = e_start + 0.5f * ev0;                          // EX + EV, hmc_state.py:80-84
                 s_red[1][q][m] = e_end + 0.5f * ev1;
-            } else {
+            } else if (mma_warp) {
                 // ---- the MMA warp: chunk c of a product is issued as soon as its 512 writers have arrived.
                 // One elected lane issues; the descriptors are base + immediate (a single thread executes ~1
                 // instruction per 4 cycles: rebuilding six 64-bit descriptors per K step cost 250 cycles per MMA in
@@ -600,7 +678,21 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                     }
                     ++pc;
                 }
+            } else {
+                // ---- the helper warps work beside the trajectory on what does not depend on it:
+                // the uniforms of this tile's particles (Philox) with the uniform-only half of the race screen ...
+                const int ht = tid - (kTcEpiThreads + 32);
+                const bool discrete = sampler == MJHMC_SAMPLER_DISCRETE;
+                for (int t = ht; t < np; t += kTcHelpers) {
+                    const Uniform3 u = draw_uniforms(p, cur + t, attempt, !discrete && p.p_r != 0.0);
+                    s_u[0][t] = u.u0; s_u[1][t] = u.u1; s_u[2][t] = u.u2;
+                    if (!discrete) s_rd[t] = race_draws(p.p_r, u.u0, u.u1, u.u2, literal_race);
+                }
+                // ... and the momentum refresh of the R movers of the tile before (their momenta were stored before that
+                // tile's closing barrier; nothing reads them before the next iteration)
+                if (pend_nr > 0) refresh_jobs(s_rlist[pend_buf], pend_nr, pend_cur, attempt, ht, kTcHelpers);
             }
+            pend_nr = 0;
             TCX_MARK(2)
             __syncthreads();
             TCX_MARK(3)
@@ -624,7 +716,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                     } else {
                         Hflf = Hcc[cur + tid];
                     }
-                    const Decision dc = decide_mj(p, cur + tid, attempt, (double)(H - Hl), (double)(H - Hflf), p.dwell != nullptr || (it + 1 == p.n_iter && p.dwell_last != nullptr));
+                    const Decision dc = decide_mj_s(p.p_r, s_u[0][tid], s_u[1][tid], s_u[2][tid], s_rd[tid], (double)(H - Hl), (double)(H - Hflf), p.dwell != nullptr || (it + 1 == p.n_iter && p.dwell_last != nullptr));
                     if (dc.fail) report_failure(p, it);
                     else {
                         ok = 1; choice = dc.choice; dwell = dc.dwell;
@@ -636,7 +728,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                     p.ca_out[cur + tid] = (uint8_t)(ok ? cflags : (need ? (cflags & ~2u) : cflags));
                     ((float*)p.Hc_out)[cur + tid] = Hc;
                 } else if (sampler == MJHMC_SAMPLER_CONTINUOUS_TIME) {
-                    const Decision dc = decide_ct(p, cur + tid, attempt, (double)(H - Hl), p.dwell != nullptr || (it + 1 == p.n_iter && p.dwell_last != nullptr));
+                    const Decision dc = decide_ct_s(p.p_r, s_u[0][tid], s_u[1][tid], s_u[2][tid], s_rd[tid], (double)(H - Hl), p.dwell != nullptr || (it + 1 == p.n_iter && p.dwell_last != nullptr));
                     if (dc.fail) report_failure(p, it);
                     else {
                         ok = 1; choice = dc.choice; dwell = dc.dwell;
@@ -645,15 +737,14 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                         else { refresh = 1; n_r += 1; }
                     }
                 } else {
-                    const Decision dc = decide_discrete(p, cur + tid, attempt, (double)(H - Hl), s_coin != 0);
-                    ok = 1; choice = dc.choice;
+                    ok = 1; choice = decide_discrete_s(p.p_flip, s_u[0][tid], s_u[1][tid], (double)(H - Hl), s_coin != 0);
                     const bool acc = choice & 1u, fl = choice & 2u;
                     if (acc) take = 2;
                     flip = fl; refresh = (choice & 4u) ? 1u : 0u;
                     n_l += (acc && fl); n_f += (fl && !acc); n_fl += (acc && !fl); n_r += refresh;
                 }
                 s_code[tid] = take | (flip << 2) | (refresh << 3) | (ok << 4);
-                if (ok && refresh) s_rlist[atomicAdd(&s_nr, 1)] = tid;
+                if (ok && refresh) s_rlist[tb][atomicAdd(&s_nr[tb], 1)] = tid;
                 if (ok) {
                     if (p.dwell) p.dwell[(long long)it * p.n + cur + tid] = dwell;
                     if (p.choice) p.choice[(long long)it * p.n + cur + tid] = (uint8_t)choice;
@@ -668,16 +759,14 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                 const unsigned int code = s_code[m];
                 const unsigned int tk = code & 3u;
                 const bool fp = code & 4u, okk = code & 16u;
-                // a particle that did not take the trajectory keeps its state: fetch it in one batch of independent
-                // loads (load -> store pairs element by element serialise on the memory latency: Xout may alias Xin)
+                // a particle that did not take the trajectory keeps its state: it is still in the stash
                 if (!(okk && tk)) {
 #pragma unroll
                     for (int c = 0; c < kTcCPT; ++c) {
                         const int kc = tc_core(c, q);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const int k = kc * 8 + j;
-                            if (k < d) { x[c][j] = Xc[(long long)k * p.ld + i]; v[c][j] = Vc[(long long)k * p.ld + i]; }
+                            if (kc * 8 + j < d) { x[c][j] = stX[(kc * 8 + j) * kTcRows + m]; v[c][j] = stV[(kc * 8 + j) * kTcRows + m]; }
                         }
                     }
                 } else if (tk == 2) {
@@ -687,43 +776,41 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                         for (int j = 0; j < 8; ++j) v[c][j] = -v[c][j];
                 }
                 const float vs = (okk && fp) ? -1.0f : 1.0f;
+                const bool rec = okk && p.samples != nullptr;
 #pragma unroll
                 for (int c = 0; c < kTcCPT; ++c) {
                     const int kc = tc_core(c, q);
+                    const long long o = (long long)(kc * 8) * p.ld + i;
+                    float* qx = Xo + o;
+                    float* qv = Vo + o;
+                    float* qs = (float*)p.samples + (long long)(kc * 8) * p.s_stride_k + (long long)it * p.s_stride_it + i;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int k = kc * 8 + j;
-                        if (k < d) {
-                            const long long o = (long long)k * p.ld + i;
-                            Xo[o] = x[c][j];
-                            Vo[o] = vs * v[c][j];
-                            if (okk && p.samples) ((float*)p.samples)[(long long)k * p.s_stride_k + (long long)it * p.s_stride_it + i] = x[c][j];
+                        if (kc * 8 + j < d) {
+                            qx[(long long)j * p.ld] = x[c][j];
+                            qv[(long long)j * p.ld] = vs * v[c][j];
+                            if (rec) qs[(long long)j * p.s_stride_k] = x[c][j];
                         }
                     }
                 }
             }
-            // ---- momentum refresh (hmc_state.py:121-129) of the R movers: all threads share the Box-Muller pairs of the
-            // few refreshed particles of the tile (one thread per particle slice would run the 16 pairs of its slice in
-            // warps where a single lane has an R move)
-            if (s_nr > 0) {
-                const float rk = (float)p.r_keep, rm = (float)p.r_mix;
-                __syncthreads();                                                   // after the momenta written above (partial refresh reads them)
-                const int npairs = (d + 1) >> 1, njobs = s_nr * npairs;
-                for (int job = tid; job < njobs; job += kTcThreads) {
-                    const int r = job / npairs, pr = job - r * npairs;
-                    const long long ip = cur + s_rlist[r];
-                    double z0, z1;
-                    normal_pair(p, ip, attempt, pr, d, z0, z1);
-                    const long long o0 = (long long)(2 * pr) * p.ld + ip;
-                    Vo[o0] = (rk != 0.0f ? Vo[o0] * rk : 0.0f) + (float)z0 * rm;  // hmc_state.py:126
-                    if (2 * pr + 1 < d) {
-                        const long long o1 = o0 + p.ld;
-                        Vo[o1] = (rk != 0.0f ? Vo[o1] * rk : 0.0f) + (float)z1 * rm;
-                    }
+            TCX_MARK(5)
+            // ---- momentum refresh (hmc_state.py:121-129) of the R movers.  A few per tile (the continuous-time samplers):
+            // left to the helper warps, beside the trajectory of the next tile.  Many (the batch-wide coin of the discrete
+            // samplers): all threads share the Box-Muller pairs now (one thread per particle slice would run the 16 pairs of
+            // its slice in warps where a single lane has an R move).
+            {
+                const int nr = s_nr[tb];                                           // final since the barrier after the decisions
+                if (nr > kTcDeferMax) {
+                    __syncthreads();                                               // after the momenta written above (partial refresh reads them)
+                    refresh_jobs(s_rlist[tb], nr, cur, attempt, tid, kTcThreads);
+                } else if (nr > 0) {
+                    pend_nr = nr; pend_buf = tb; pend_cur = cur;
                 }
             }
-            __syncthreads();                       // the tables, s_red and the A planes are reused by the next tile
-            TCX_MARK(5)
+            __syncthreads();                       // the tables, s_red, the stash and the A planes are reused by the next tile
+            if (cur + np < r1) stash_bulk = stash_issue(Xc, Vc, cur + np);
+            TCX_MARK(6)
 #ifdef TCX_TRACE
             if (blockIdx.x == 0 && tile_no == 3 && tid == 0) {
                 for (int pr = 0; pr < 12; ++pr) {
@@ -735,7 +822,16 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
             ++tile_no;
 #endif
             cur += np;
+            tb ^= 1;
         }
+        // the last tile's R movers: before the next iteration (or the host) reads their momenta
+        if (pend_nr > 0) {
+            refresh_jobs(s_rlist[pend_buf], pend_nr, pend_cur, attempt, tid, kTcThreads);
+            pend_nr = 0;
+        }
+        // this iteration's state (generic-proxy stores) is read by the bulk copies (async proxy) of the next one
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __syncthreads();
     }
     if (p.n_iter == 0) {
         for (long long i = r0 + tid; i < r1; i += kTcThreads)
@@ -751,7 +847,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
 
 #ifdef TCX_TIMING
     if (blockIdx.x == 0 && (tid == 0 || tid == 130 || tid == 300 || tid == 512))
-        printf("tid %d: plan %lld load %lld traj %lld sync %lld decide %lld apply %lld | w0 %lld w1 %lld w2 %lld w3 %lld issue %lld\n", tid, tph[0], tph[1], tph[2], tph[3], tph[4], tph[5], tw[0], tw[1], tw[2], tw[3], tw[4]);
+        printf("tid %d: plan %lld load %lld traj %lld sync %lld decide %lld apply %lld refresh %lld | w0 %lld w1 %lld w2 %lld w3 %lld issue %lld\n", tid, tph[0], tph[1], tph[2], tph[3], tph[4], tph[5], tph[6], tw[0], tw[1], tw[2], tw[3], tw[4]);
 #endif
     // ---- teardown
     tc_fence_before();
@@ -789,7 +885,7 @@ template <bool POT, int PC>
 static cudaError_t launch_tc_T(const LaunchParams& p, cudaStream_t stream) {
     int P, nc;
     tc_shape(p.d, P, nc);
-    const size_t smem = 3 * (size_t)nc * nc * 128 + (POT ? kTcTabs * P * 4 : 0) + 1024;
+    const size_t smem = 3 * (size_t)nc * nc * 128 + (POT ? kTcTabs * P * 4 : 0) + 1024 + 128 + 2 * (size_t)P * kTcRows * 4;
     static int sms = 0;
     if (!sms) {
         int dev = 0;
