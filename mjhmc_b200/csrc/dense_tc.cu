@@ -74,6 +74,14 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// shared -> global bulk copy (TMA store) in the thread's current bulk group
+__device__ __forceinline__ void tma_bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void helper_bar() { asm volatile("bar.sync 1, %0;" ::"n"(96) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -344,17 +352,22 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     };
     const bool bulk_base_ok = (p.ld & 3) == 0 &&
         ((((uintptr_t)p.Xin) | ((uintptr_t)p.Vin) | ((uintptr_t)p.Xout) | ((uintptr_t)p.Vout)) & 15u) == 0;
-    // one bulk copy per row of the two boxes (threads 0 .. 2d-1); false: the tile fills the stash with plain loads
+    // one bulk copy per row of the two boxes, issued by the helper threads; false: the tile fills the stash with plain loads
+    const int ht = tid - (kTcEpiThreads + 32);     // helper thread index (< 0: not a helper)
     auto stash_issue = [&](const float* Xs, const float* Vs, long long c0) -> bool {
         const bool ok = bulk_base_ok && (c0 & 3) == 0 && c0 + kTcRows <= p.n;
-        if (ok && tid < 2 * d) {
-            if (tid == 0) mbar_expect_tx(&bar_st, (uint32_t)(2 * d * kTcRows * 4));
-            const int k = tid < d ? tid : tid - d;
+        if (ok && ht >= 0) {
+            if (ht == 0) mbar_expect_tx(&bar_st, (uint32_t)(2 * d * kTcRows * 4));
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            tma_bulk_g2s((tid < d ? stX : stV) + k * kTcRows, (tid < d ? Xs : Vs) + (long long)k * p.ld + c0, kTcRows * 4, &bar_st);
+            for (int r = ht; r < 2 * d; r += kTcHelpers) {
+                const int k = r < d ? r : r - d;
+                tma_bulk_g2s((r < d ? stX : stV) + k * kTcRows, (r < d ? Xs : Vs) + (long long)k * p.ld + c0, kTcRows * 4, &bar_st);
+            }
         }
         return ok;
     };
+    const bool bulk_samples_ok = p.samples == nullptr ||
+        ((((uintptr_t)p.samples) & 15u) == 0 && (p.s_stride_k & 3) == 0 && (p.s_stride_it & 3) == 0);
     uint32_t st_par = 0;                           // parity of the stash fill the next bulk-filled tile waits for
     bool stash_bulk = false;                       // the coming tile's stash was requested with bulk copies
     int tb = 0;                                    // tile parity: which s_rlist / s_nr this tile fills
@@ -421,6 +434,8 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                 st_par ^= 1u;
             } else {
                 // rows that are not 16-byte aligned, or the ragged end of the cloud: plain loads
+                if (ht >= 0) bulk_wait_read();      // the bulk stores of the tile before may still be reading the stash
+                __syncthreads();
                 for (int idx = tid; idx < 2 * d * kTcRows; idx += kTcThreads) {
                     const int a = idx / (d * kTcRows), rem = idx - a * (d * kTcRows);
                     const int k = rem / kTcRows, mm = rem - k * kTcRows;
@@ -681,7 +696,6 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
             } else {
                 // ---- the helper warps work beside the trajectory on what does not depend on it:
                 // the uniforms of this tile's particles (Philox) with the uniform-only half of the race screen ...
-                const int ht = tid - (kTcEpiThreads + 32);
                 const bool discrete = sampler == MJHMC_SAMPLER_DISCRETE;
                 for (int t = ht; t < np; t += kTcHelpers) {
                     const Uniform3 u = draw_uniforms(p, cur + t, attempt, !discrete && p.p_r != 0.0);
@@ -690,7 +704,12 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                 }
                 // ... and the momentum refresh of the R movers of the tile before (their momenta were stored before that
                 // tile's closing barrier; nothing reads them before the next iteration)
-                if (pend_nr > 0) refresh_jobs(s_rlist[pend_buf], pend_nr, pend_cur, attempt, ht, kTcHelpers);
+                if (pend_nr > 0) {
+                    bulk_wait_all();               // that tile's bulk stores (issued by these warps) have reached memory
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    helper_bar();
+                    refresh_jobs(s_rlist[pend_buf], pend_nr, pend_cur, attempt, ht, kTcHelpers);
+                }
             }
             pend_nr = 0;
             TCX_MARK(2)
@@ -751,65 +770,87 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                     if (p.dwell_last && sampler != MJHMC_SAMPLER_DISCRETE) p.dwell_last[cur + tid] = dwell;
                 }
             }
-            __syncthreads();
+            const int any_fail = __syncthreads_or(mine && !ok);
             TCX_MARK(4)
 
-            // ---- apply: my slice of my particle's new state goes to the output arrays
+            // ---- apply: the new state of the tile's particles is assembled in the stash (a particle that did not take its
+            // trajectory is already there) and leaves as one bulk copy (TMA store) per row -- X, V and the sample record --
+            // issued by the helper warps while the other warps plan the next tile.  (Per-thread stores: 84 scalar stores
+            // with 64-bit row addresses each, 19k cycles per tile.)
             if (is_l) {
                 const unsigned int code = s_code[m];
                 const unsigned int tk = code & 3u;
                 const bool fp = code & 4u, okk = code & 16u;
-                // a particle that did not take the trajectory keeps its state: it is still in the stash
-                if (!(okk && tk)) {
+                if (okk && tk) {
+                    const float vs = ((tk == 2) != fp) ? -1.0f : 1.0f;
 #pragma unroll
                     for (int c = 0; c < kTcCPT; ++c) {
                         const int kc = tc_core(c, q);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            if (kc * 8 + j < d) { x[c][j] = stX[(kc * 8 + j) * kTcRows + m]; v[c][j] = stV[(kc * 8 + j) * kTcRows + m]; }
+                            if (kc * 8 + j < d) { stX[(kc * 8 + j) * kTcRows + m] = x[c][j]; stV[(kc * 8 + j) * kTcRows + m] = vs * v[c][j]; }
                         }
                     }
-                } else if (tk == 2) {
+                } else if (okk && fp) {
 #pragma unroll
-                    for (int c = 0; c < kTcCPT; ++c)
+                    for (int c = 0; c < kTcCPT; ++c) {
+                        const int kc = tc_core(c, q);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[c][j] = -v[c][j];
-                }
-                const float vs = (okk && fp) ? -1.0f : 1.0f;
-                const bool rec = okk && p.samples != nullptr;
-#pragma unroll
-                for (int c = 0; c < kTcCPT; ++c) {
-                    const int kc = tc_core(c, q);
-                    const long long o = (long long)(kc * 8) * p.ld + i;
-                    float* qx = Xo + o;
-                    float* qv = Vo + o;
-                    float* qs = (float*)p.samples + (long long)(kc * 8) * p.s_stride_k + (long long)it * p.s_stride_it + i;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (kc * 8 + j < d) {
-                            qx[(long long)j * p.ld] = x[c][j];
-                            qv[(long long)j * p.ld] = vs * v[c][j];
-                            if (rec) qs[(long long)j * p.s_stride_k] = x[c][j];
+                        for (int j = 0; j < 8; ++j) {
+                            if (kc * 8 + j < d) stV[(kc * 8 + j) * kTcRows + m] = -stV[(kc * 8 + j) * kTcRows + m];
                         }
                     }
                 }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
+            __syncthreads();                       // the stash is final; the tables, s_red and the A planes are free for the next tile
             TCX_MARK(5)
-            // ---- momentum refresh (hmc_state.py:121-129) of the R movers.  A few per tile (the continuous-time samplers):
-            // left to the helper warps, beside the trajectory of the next tile.  Many (the batch-wide coin of the discrete
-            // samplers): all threads share the Box-Muller pairs now (one thread per particle slice would run the 16 pairs of
-            // its slice in warps where a single lane has an R move).
             {
+                const bool rec = p.samples != nullptr;
+                const bool bulk_out = bulk_base_ok && bulk_samples_ok && (cur & 3) == 0 && (np & 3) == 0 && !(rec && any_fail);
+                if (bulk_out) {
+                    if (ht >= 0) {
+                        const int nrow = (rec ? 3 : 2) * d;
+                        for (int r = ht; r < nrow; r += kTcHelpers) {
+                            const int a = r / d, k = r - a * d;
+                            float* dst = a == 0 ? Xo + (long long)k * p.ld + cur
+                                       : a == 1 ? Vo + (long long)k * p.ld + cur
+                                       : (float*)p.samples + (long long)k * p.s_stride_k + (long long)it * p.s_stride_it + cur;
+                            tma_bulk_s2g(dst, (a == 1 ? stV : stX) + k * kTcRows, (uint32_t)np * 4u);
+                        }
+                        bulk_commit();
+                    }
+                } else {
+                    // ragged or unaligned tile, or a failed particle (its sample is not recorded): plain stores
+                    for (int idx = tid; idx < d * np; idx += kTcThreads) {
+                        const int k = idx / np, mm = idx - k * np;
+                        const long long o = (long long)k * p.ld + cur + mm;
+                        const float xv = stX[k * kTcRows + mm];
+                        Xo[o] = xv;
+                        Vo[o] = stV[k * kTcRows + mm];
+                        if (rec && (s_code[mm] & 16u)) ((float*)p.samples)[(long long)k * p.s_stride_k + (long long)it * p.s_stride_it + cur + mm] = xv;
+                    }
+                    __syncthreads();
+                }
+                // ---- momentum refresh (hmc_state.py:121-129) of the R movers.  A few per tile (the continuous-time
+                // samplers): left to the helper warps, beside the trajectory of the next tile.  Many (the batch-wide coin of
+                // the discrete samplers): all threads share the Box-Muller pairs now (one thread per particle slice would
+                // run the 16 pairs of its slice in warps where a single lane has an R move).
                 const int nr = s_nr[tb];                                           // final since the barrier after the decisions
                 if (nr > kTcDeferMax) {
-                    __syncthreads();                                               // after the momenta written above (partial refresh reads them)
+                    if (bulk_out && ht >= 0) { bulk_wait_all(); asm volatile("fence.proxy.async;" ::: "memory"); }
+                    __syncthreads();                                               // the momenta are in memory (partial refresh reads them)
                     refresh_jobs(s_rlist[tb], nr, cur, attempt, tid, kTcThreads);
                 } else if (nr > 0) {
                     pend_nr = nr; pend_buf = tb; pend_cur = cur;
                 }
+                // ---- the helper warps fetch the next tile's boxes as soon as the stores have read the stash
+                if (ht >= 0) {
+                    if (bulk_out) bulk_wait_read();
+                    helper_bar();
+                }
+                if (cur + np < r1) stash_bulk = stash_issue(Xc, Vc, cur + np);
             }
-            __syncthreads();                       // the tables, s_red, the stash and the A planes are reused by the next tile
-            if (cur + np < r1) stash_bulk = stash_issue(Xc, Vc, cur + np);
             TCX_MARK(6)
 #ifdef TCX_TRACE
             if (blockIdx.x == 0 && tile_no == 3 && tid == 0) {
@@ -825,6 +866,8 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
             tb ^= 1;
         }
         // the last tile's R movers: before the next iteration (or the host) reads their momenta
+        if (ht >= 0) { bulk_wait_all(); asm volatile("fence.proxy.async;" ::: "memory"); }
+        __syncthreads();
         if (pend_nr > 0) {
             refresh_jobs(s_rlist[pend_buf], pend_nr, pend_cur, attempt, tid, kTcThreads);
             pend_nr = 0;
