@@ -29,8 +29,11 @@
 // D0 and dEdX in D1), so the MMAs of product n+1 may overwrite nothing the epilogue of product n still reads.
 // Round 1's kernel was MMA -> epilogue -> MMA strictly serial (tensor pipe 29.7 % active).
 #include <cstdio>
+#include <cstring>
 #include <cuda_bf16.h>
+#include <cuda.h>
 #include "dense.h"
+#include "stream.h"
 
 namespace mjhmc {
 
@@ -46,6 +49,7 @@ constexpr int kTcCPT = 4;                          // 8-wide core columns per th
 constexpr int kTcTmemCols = 512;                   // two accumulators of 128 columns + three A planes of 64
 constexpr uint32_t kTcACol = 256;                  // first TMEM column of A plane 0
 constexpr uint32_t kTcPlaneCols = 64;              // TMEM columns per A plane (112 bf16 = 56 columns, padded)
+constexpr int kTcPiece = 32;                       // particle columns per TMA box of the state stash (128-byte rows)
 constexpr int kTcTabs = 5;                         // ProductOfT per-expert tables: nu+1, nu^2, b, (nu+1)/2, 1/nu^2
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -74,10 +78,22 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// shared -> global bulk copy (TMA store) in the thread's current bulk group
-__device__ __forceinline__ void tma_bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+// (dims x 32 particles) boxes of a (dims, n) array: global -> shared on an mbarrier, shared -> global in the thread's
+// current bulk group; coordinate 0 = first particle, coordinate 1 = first dim (the sample record has the iteration between)
+__device__ __forceinline__ void tma_box_g2s(void* dst_smem, const CUtensorMap* map, int c0, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst_smem)), "l"((uint64_t)map), "r"(c0), "r"(0), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tma_box_s2g(const CUtensorMap* map, int c0, const void* src_smem) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"((uint64_t)map), "r"(c0), "r"(0), "r"(smem_u32(src_smem)) : "memory");
+}
+__device__ __forceinline__ void tma_box_s2g_3d(const CUtensorMap* map, int c0, int c1, const void* src_smem) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 ::"l"((uint64_t)map), "r"(c0), "r"(c1), "r"(0), "r"(smem_u32(src_smem)) : "memory");
+}
+// tensor maps of one launch (host: launch_tc_T); ok = the four state maps exist, smp_ok = the sample-record map too
+struct TcMaps { CUtensorMap xin, vin, xout, vout, smp; int ok, smp_ok; };
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -221,7 +237,7 @@ __global__ void tc_prep_kernel(const float* __restrict__ Mx, int rows, int cols,
 // and table offset below folds to a constant), 0 = taken from the launch
 template <bool POT, int PC>
 __global__ void __launch_bounds__(kTcThreads, 1)
-dense_tc_kernel(const __grid_constant__ LaunchParams p) {
+dense_tc_kernel(const __grid_constant__ LaunchParams p, const __grid_constant__ TcMaps maps) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     __shared__ __align__(8) uint64_t bar_tma, bar_st, bar_done[kTcCPT], bar_chunk[kTcCPT];
     __shared__ uint32_t s_tmem;
@@ -244,12 +260,13 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
     const uint32_t ws_bytes = 3u * b_plane + (POT ? (uint32_t)(kTcTabs * P * 4) : 0u);
     uint8_t* B0 = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);
     const float* tab = reinterpret_cast<const float*>(B0 + 3u * b_plane);
-    // State stash: the (dims x 128 particles) boxes of X and V the tile starts from, row k at k * 128 floats.  Filled by
-    // one bulk copy (TMA) per row, issued when the tile before has let go of the stash -- beside its stores and this
-    // tile's plan -- read by the job rows (an FLF job shares the columns of its particle's L job) and again by the
-    // particles that do not take their trajectory.
+    // State stash: the (dims x 128 particles) boxes of X and V the tile starts from, as four TMA boxes of 32 particle
+    // columns each (element (k, m) at stash_at(m) + 32 k).  Filled by the helper warps when the tile before has let go of
+    // the stash -- beside this tile's plan -- read by the job rows (an FLF job shares the column of its particle's L
+    // job); the new state of the tile is assembled in it and leaves as TMA stores.
     float* const stX = reinterpret_cast<float*>(B0 + ((ws_bytes + 127u) & ~127u));
     float* const stV = stX + P * kTcRows;
+    auto stash_at = [&](int mcol) { return (mcol >> 5) * (P * kTcPiece) + (mcol & (kTcPiece - 1)); };
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool epi = tid < kTcEpiThreads;
     const bool mma_warp = warp == kTcEpiThreads / 32;
@@ -350,24 +367,24 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
             }
         }
     };
-    const bool bulk_base_ok = (p.ld & 3) == 0 &&
-        ((((uintptr_t)p.Xin) | ((uintptr_t)p.Vin) | ((uintptr_t)p.Xout) | ((uintptr_t)p.Vout)) & 15u) == 0;
-    // one bulk copy per row of the two boxes, issued by the helper threads; false: the tile fills the stash with plain loads
+    // the boxes of particles c0 .. c0 + 127 (columns past the end of the cloud arrive as zeros), issued by eight helper
+    // threads; false: the tile fills the stash with plain loads
     const int ht = tid - (kTcEpiThreads + 32);     // helper thread index (< 0: not a helper)
-    auto stash_issue = [&](const float* Xs, const float* Vs, long long c0) -> bool {
-        const bool ok = bulk_base_ok && (c0 & 3) == 0 && c0 + kTcRows <= p.n;
-        if (ok && ht >= 0) {
-            if (ht == 0) mbar_expect_tx(&bar_st, (uint32_t)(2 * d * kTcRows * 4));
+    auto stash_issue = [&](bool first_iter, long long c0) -> bool {
+        if (maps.ok && ht == 0) {                  // one thread, the tensor map named in the instruction (no address select)
+            mbar_expect_tx(&bar_st, (uint32_t)(2 * kTcRows * d * 4));
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            for (int r = ht; r < 2 * d; r += kTcHelpers) {
-                const int k = r < d ? r : r - d;
-                tma_bulk_g2s((r < d ? stX : stV) + k * kTcRows, (r < d ? Xs : Vs) + (long long)k * p.ld + c0, kTcRows * 4, &bar_st);
+#pragma unroll
+            for (int piece = 0; piece < kTcRows / kTcPiece; ++piece) {
+                float* dx = stX + piece * (P * kTcPiece);
+                float* dv = stV + piece * (P * kTcPiece);
+                const int cc = (int)c0 + piece * kTcPiece;
+                if (first_iter) { tma_box_g2s(dx, &maps.xin, cc, &bar_st); tma_box_g2s(dv, &maps.vin, cc, &bar_st); }
+                else { tma_box_g2s(dx, &maps.xout, cc, &bar_st); tma_box_g2s(dv, &maps.vout, cc, &bar_st); }
             }
         }
-        return ok;
+        return maps.ok != 0;
     };
-    const bool bulk_samples_ok = p.samples == nullptr ||
-        ((((uintptr_t)p.samples) & 15u) == 0 && (p.s_stride_k & 3) == 0 && (p.s_stride_it & 3) == 0);
     uint32_t st_par = 0;                           // parity of the stash fill the next bulk-filled tile waits for
     bool stash_bulk = false;                       // the coming tile's stash was requested with bulk copies
     int tb = 0;                                    // tile parity: which s_rlist / s_nr this tile fills
@@ -383,7 +400,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
         float* Xo = (float*)p.Xout;
         float* Vo = (float*)p.Vout;
         if (sampler == MJHMC_SAMPLER_DISCRETE && tid == 0) s_coin = draw_coin(p, attempt) < p.p_r;
-        if (r0 < r1) stash_bulk = stash_issue(Xc, Vc, r0);
+        if (r0 < r1) stash_bulk = stash_issue(it == 0, r0);
 
         for (long long cur = r0; cur < r1;) {
             // ---- plan the tile: particles cur .. cur+np-1 with np + #FLF jobs <= 128
@@ -408,7 +425,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                 s_flf_row[tid] = -1;
             }
             int np = __syncthreads_count(tid < kTcRows && valid && incl <= kTcRows);
-            // tiles start at multiples of 4 particles (16-byte aligned rows for the bulk copies of the state stash)
+            // tiles start at multiples of 4 particles: the first element of a TMA box has to be 16-byte aligned
             if (cur + np < r1) np &= ~3;
             const bool mine = tid < np;                                     // lead thread of an L job
             if (mine && need) {
@@ -424,7 +441,6 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
             // ---- my job: row m -> (particle, sign)
             const bool is_l = epi && m < np, is_flf = epi && m >= np && m < nrows;
             const int part = is_l ? m : (is_flf ? s_row_part[m] : 0);
-            const long long i = cur + part;
             const float sign = is_flf ? -1.0f : 1.0f;
             const bool live = is_l || is_flf;
 
@@ -433,7 +449,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                 if (epi) mbar_wait(&bar_st, st_par);
                 st_par ^= 1u;
             } else {
-                // rows that are not 16-byte aligned, or the ragged end of the cloud: plain loads
+                // no tensor maps (rows that are not 16-byte aligned): plain loads
                 if (ht >= 0) bulk_wait_read();      // the bulk stores of the tile before may still be reading the stash
                 __syncthreads();
                 for (int idx = tid; idx < 2 * d * kTcRows; idx += kTcThreads) {
@@ -441,7 +457,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                     const int k = rem / kTcRows, mm = rem - k * kTcRows;
                     const long long gi = cur + mm;
                     const float val = gi < p.n ? (a ? Vc : Xc)[(long long)k * p.ld + gi] : 0.0f;
-                    (a ? stV : stX)[k * kTcRows + mm] = val;
+                    (a ? stV : stX)[stash_at(mm) + k * kTcPiece] = val;
                 }
                 __syncthreads();
             }
@@ -449,14 +465,15 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
             if (epi) {
                 // ---- my slice of (x, +-v) from the stash
                 float ev0 = 0.0f;
+                const int sa = stash_at(part);
 #pragma unroll
                 for (int c = 0; c < kTcCPT; ++c) {
                     const int kc = tc_core(c, q);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const bool in = live && kc * 8 + j < d;
-                        x[c][j] = in ? stX[(kc * 8 + j) * kTcRows + part] : 0.0f;
-                        v[c][j] = in ? stV[(kc * 8 + j) * kTcRows + part] : 0.0f;
+                        x[c][j] = in ? stX[sa + (kc * 8 + j) * kTcPiece] : 0.0f;
+                        v[c][j] = in ? stV[sa + (kc * 8 + j) * kTcPiece] : 0.0f;
                     }
                 }
 #pragma unroll
@@ -781,6 +798,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                 const unsigned int code = s_code[m];
                 const unsigned int tk = code & 3u;
                 const bool fp = code & 4u, okk = code & 16u;
+                const int sm_ = stash_at(m);
                 if (okk && tk) {
                     const float vs = ((tk == 2) != fp) ? -1.0f : 1.0f;
 #pragma unroll
@@ -788,7 +806,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                         const int kc = tc_core(c, q);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            if (kc * 8 + j < d) { stX[(kc * 8 + j) * kTcRows + m] = x[c][j]; stV[(kc * 8 + j) * kTcRows + m] = vs * v[c][j]; }
+                            if (kc * 8 + j < d) { stX[sm_ + (kc * 8 + j) * kTcPiece] = x[c][j]; stV[sm_ + (kc * 8 + j) * kTcPiece] = vs * v[c][j]; }
                         }
                     }
                 } else if (okk && fp) {
@@ -797,7 +815,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                         const int kc = tc_core(c, q);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            if (kc * 8 + j < d) stV[(kc * 8 + j) * kTcRows + m] = -stV[(kc * 8 + j) * kTcRows + m];
+                            if (kc * 8 + j < d) stV[sm_ + (kc * 8 + j) * kTcPiece] = -stV[sm_ + (kc * 8 + j) * kTcPiece];
                         }
                     }
                 }
@@ -807,27 +825,37 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
             TCX_MARK(5)
             {
                 const bool rec = p.samples != nullptr;
-                const bool bulk_out = bulk_base_ok && bulk_samples_ok && (cur & 3) == 0 && (np & 3) == 0 && !(rec && any_fail);
-                if (bulk_out) {
-                    if (ht >= 0) {
-                        const int nrow = (rec ? 3 : 2) * d;
-                        for (int r = ht; r < nrow; r += kTcHelpers) {
-                            const int a = r / d, k = r - a * d;
-                            float* dst = a == 0 ? Xo + (long long)k * p.ld + cur
-                                       : a == 1 ? Vo + (long long)k * p.ld + cur
-                                       : (float*)p.samples + (long long)k * p.s_stride_k + (long long)it * p.s_stride_it + cur;
-                            tma_bulk_s2g(dst, (a == 1 ? stV : stX) + k * kTcRows, (uint32_t)np * 4u);
+                // Boxes that leave by TMA.  A box that reaches past this tile also rewrites the state the stash holds for
+                // the first particles of the NEXT tile: unchanged values (or, in the first iteration, the input copied to
+                // the output buffer, and a stale sample) that the next tile's own stores replace -- in that order, because
+                // the helpers wait for their earlier stores before they issue new ones.  At the end of the CTA's range the
+                // neighbour's particles follow, so a partial box goes out with plain stores; so does a tile with a failed
+                // particle (its sample is not recorded).
+                int n_box = 0;
+                if (maps.ok && !(rec && (any_fail || !maps.smp_ok))) n_box = (cur + np < r1) ? (np + kTcPiece - 1) / kTcPiece : np / kTcPiece;
+                if (ht >= 0 && n_box > 0) {
+                    bulk_wait_all();
+                    helper_bar();
+                    if (ht == 0) {
+                        for (int piece = 0; piece < n_box; ++piece) {
+                            const int c0 = (int)cur + piece * kTcPiece;
+                            tma_box_s2g(&maps.xout, c0, stX + piece * (P * kTcPiece));
+                            tma_box_s2g(&maps.vout, c0, stV + piece * (P * kTcPiece));
+                            if (rec) tma_box_s2g_3d(&maps.smp, c0, it, stX + piece * (P * kTcPiece));
                         }
-                        bulk_commit();
                     }
-                } else {
-                    // ragged or unaligned tile, or a failed particle (its sample is not recorded): plain stores
-                    for (int idx = tid; idx < d * np; idx += kTcThreads) {
-                        const int k = idx / np, mm = idx - k * np;
+                    bulk_commit();
+                }
+                const bool bulk_out = n_box > 0;
+                const int c_plain = n_box * kTcPiece;
+                if (c_plain < np) {
+                    const int w = np - c_plain;
+                    for (int idx = tid; idx < d * w; idx += kTcThreads) {
+                        const int k = idx / w, mm = c_plain + (idx - k * w);
                         const long long o = (long long)k * p.ld + cur + mm;
-                        const float xv = stX[k * kTcRows + mm];
+                        const float xv = stX[stash_at(mm) + k * kTcPiece];
                         Xo[o] = xv;
-                        Vo[o] = stV[k * kTcRows + mm];
+                        Vo[o] = stV[stash_at(mm) + k * kTcPiece];
                         if (rec && (s_code[mm] & 16u)) ((float*)p.samples)[(long long)k * p.s_stride_k + (long long)it * p.s_stride_it + cur + mm] = xv;
                     }
                     __syncthreads();
@@ -849,7 +877,7 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p) {
                     if (bulk_out) bulk_wait_read();
                     helper_bar();
                 }
-                if (cur + np < r1) stash_bulk = stash_issue(Xc, Vc, cur + np);
+                if (cur + np < r1) stash_bulk = stash_issue(it == 0, cur + np);
             }
             TCX_MARK(6)
 #ifdef TCX_TRACE
@@ -940,7 +968,22 @@ static cudaError_t launch_tc_T(const LaunchParams& p, cudaStream_t stream) {
     long long blocks = (p.n + 95) / 96;            // ~one tile of jobs per CTA at the least
     if (blocks > sms) blocks = sms;
     if (blocks < 1) blocks = 1;
-    dense_tc_kernel<POT, PC><<<(unsigned)blocks, kTcThreads, smem, stream>>>(p);
+    // tensor maps of the state arrays and the sample record: (dims x 32 particles) boxes
+    TcMaps maps;
+    memset(&maps, 0, sizeof maps);
+    {
+        const long long dims[2] = {p.n, p.d}, strides[1] = {p.ld};
+        const int box[2] = {kTcPiece, p.d};
+        maps.ok = make_tensor_map_f32(&maps.xin, p.Xin, 2, dims, strides, box) && make_tensor_map_f32(&maps.vin, p.Vin, 2, dims, strides, box) &&
+                  make_tensor_map_f32(&maps.xout, p.Xout, 2, dims, strides, box) && make_tensor_map_f32(&maps.vout, p.Vout, 2, dims, strides, box);
+        maps.smp_ok = 1;
+        if (maps.ok && p.samples && p.n_iter > 0) {
+            const long long dims3[3] = {p.n, p.n_iter, p.d}, strides3[2] = {p.s_stride_it, p.s_stride_k};
+            const int box3[3] = {kTcPiece, 1, p.d};
+            maps.smp_ok = make_tensor_map_f32(&maps.smp, p.samples, 3, dims3, strides3, box3);
+        }
+    }
+    dense_tc_kernel<POT, PC><<<(unsigned)blocks, kTcThreads, smem, stream>>>(p, maps);
     return cudaGetLastError();
 }
 

@@ -53,6 +53,31 @@ static bool make_map(CUtensorMap* m, const void* base, int dtype, long long n, l
 
 static int g_force_no_tma = 0;
 
+// fp32 array of `rank` dims (dim 0 contiguous), strides in elements for dims 1.., box extents per dim; false when the
+// array cannot be described (alignment, sizes) or TMA is switched off for the tests
+bool make_tensor_map_f32(CUtensorMap* m, const void* base, int rank, const long long* dims, const long long* strides,
+                         const int* box) {
+    memset(m, 0, sizeof *m);
+    PFN_cuTensorMapEncodeTiled enc = encode_fn();
+    if (!enc || g_force_no_tma || rank < 2 || rank > 3 || ((uintptr_t)base & 15u)) return false;
+    cuuint64_t gdim[3];
+    cuuint64_t gstride[2];
+    cuuint32_t bx[3], estr[3] = {1, 1, 1};
+    for (int k = 0; k < rank; ++k) {
+        if (dims[k] <= 0 || dims[k] > 0x7fffffffLL || box[k] < 1 || box[k] > 256) return false;
+        gdim[k] = (cuuint64_t)dims[k];
+        bx[k] = (cuuint32_t)box[k];
+        if (k) {
+            if (strides[k - 1] <= 0 || (strides[k - 1] * 4) % 16) return false;
+            gstride[k - 1] = (cuuint64_t)strides[k - 1] * 4u;
+        }
+    }
+    if ((box[0] * 4) % 16) return false;
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstride, bx, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 cudaError_t stream_make_maps(const LaunchParams& p, int dtype, int P, int rows, CUtensorMap* mx, CUtensorMap* mv,
                              int* use_tma) {
     memset(mx, 0, sizeof *mx);
