@@ -418,7 +418,7 @@ dense_sample_kernel(const __grid_constant__ LaunchParams p) {
                     const long long i = pi[e];
                     const unsigned int tk = cd & 3u, fp = (cd >> 2) & 1u, rf = (cd >> 3) & 1u, okc = (cd >> 4) & 1u;
                     const bool took = okc && tk;
-                    if (__any_sync(0xffffffffu, lcol && !took)) {
+                    if (lcol && !took) {
 #pragma unroll
                         for (int mt = 0; mt < MT; ++mt) {
                             const long long o = (long long)min(mt * 8 + ar, d - 1) * p.ld + i;

@@ -24,7 +24,10 @@ namespace mjhmc {
 
 constexpr int kStreamThreads = 256;
 constexpr int kStreamWarps = kStreamThreads / 32;
-constexpr int kStreamMaxStages = 4;
+#ifndef MJ_STREAM_MAX_STAGES
+#define MJ_STREAM_MAX_STAGES 4
+#endif
+constexpr int kStreamMaxStages = MJ_STREAM_MAX_STAGES;
 constexpr int kStreamRed = 3;              // partial sums per thread: H, H_L, H_FLF (this thread's dims)
 
 struct StreamCfg {
@@ -63,7 +66,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "SMBAR_WAIT:\n"
+#ifdef MJ_STREAM_WAIT_HINT
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+#endif
         "@p bra SMBAR_DONE;\n"
         "bra SMBAR_WAIT;\n"
         "SMBAR_DONE:\n"
