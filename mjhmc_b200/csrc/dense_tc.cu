@@ -828,11 +828,12 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p, const __grid_constant__ 
                 // Boxes that leave by TMA.  A box that reaches past this tile also rewrites the state the stash holds for
                 // the first particles of the NEXT tile: unchanged values (or, in the first iteration, the input copied to
                 // the output buffer, and a stale sample) that the next tile's own stores replace -- in that order, because
-                // the helpers wait for their earlier stores before they issue new ones.  At the end of the CTA's range the
-                // neighbour's particles follow, so a partial box goes out with plain stores; so does a tile with a failed
-                // particle (its sample is not recorded).
+                // the helpers wait for their earlier stores before they issue new ones.  A box that would reach past the end
+                // of the CTA's range (the neighbour's particles) is not sent: those columns go out with plain stores; so
+                // does a tile with a failed particle (its sample is not recorded).
                 int n_box = 0;
-                if (maps.ok && !(rec && (any_fail || !maps.smp_ok))) n_box = (cur + np < r1) ? (np + kTcPiece - 1) / kTcPiece : np / kTcPiece;
+                if (maps.ok && !(rec && (any_fail || !maps.smp_ok)))
+                    n_box = (int)min((long long)((np + kTcPiece - 1) / kTcPiece), (r1 - cur) / kTcPiece);   // whole boxes inside the range
                 if (ht >= 0 && n_box > 0) {
                     bulk_wait_all();
                     helper_bar();
@@ -849,6 +850,9 @@ dense_tc_kernel(const __grid_constant__ LaunchParams p, const __grid_constant__ 
                 const bool bulk_out = n_box > 0;
                 const int c_plain = n_box * kTcPiece;
                 if (c_plain < np) {
+                    // the boxes of the tile before may still be in flight, and they cover the first columns of this tile
+                    if (ht >= 0) { bulk_wait_all(); asm volatile("fence.proxy.async;" ::: "memory"); }
+                    __syncthreads();
                     const int w = np - c_plain;
                     for (int idx = tid; idx < d * w; idx += kTcThreads) {
                         const int k = idx / w, mm = c_plain + (idx - k * w);

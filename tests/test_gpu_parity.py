@@ -373,6 +373,71 @@ def test_dense_float32_single_iteration_from_oracle_state(dist_name):
     assert flips <= 6, flips
 
 
+@pytest.mark.parametrize("kind", ["MarkovJumpHMC", "ContinuousTimeHMC", "ControlHMC"])
+@pytest.mark.parametrize("dist_name,d,N", [("Gaussian", 100, 60000), ("ProductOfT", 36, 40004)])
+def test_dense_float32_tma_boxes_equal_plain_loads_and_stores(kind, dist_name, d, N):
+    """The tcgen05 kernel moves the state of a tile through a shared-memory stash with TMA tensor boxes (boxes that
+    reach past a tile rewrite the unchanged state of the next tile's first particles, partial boxes at the end of a
+    CTA's range leave with plain stores); without tensor maps the same stash is filled and emptied with plain loads and
+    stores.  Several tiles per CTA, several iterations per launch, dwelling times and sample record: bit-identical."""
+    from mjhmc_b200 import _lib
+    from mjhmc_b200.samplers import markov_jump_hmc as S
+    lib = _lib.load()
+    hp = dict(epsilon=0.12, beta=0.4, num_leapfrog_steps=2)
+    extra = dict(resample=False) if kind in ("ContinuousTimeHMC", "MarkovJumpHMC") else {}
+    out = []
+    _, _, X0 = _dense_case(dist_name, d, N, np.random.RandomState(9))
+    V0 = np.random.RandomState(10).randn(d, N)
+    for tma in (1, 0):
+        dist, _, _ = _dense_case(dist_name, d, N, np.random.RandomState(9))
+        helpers.pin_init(dist, X0)
+        lib.mjhmc_stream_set_tma(tma)
+        try:
+            s = getattr(S, kind)(distribution=dist, V=V0, seed=21, dtype="float32", **hp, **extra)
+            assert s._engine.fused
+            X = s.sample(3)
+            rec = [X, s.state.X.copy(), s.state.V.copy(), np.array(_counters(s, dist))]
+            if extra:
+                rec.append(np.asarray(s.dwelling_times).copy())
+            X2 = s.sample(2)                      # a second launch starts from the state the first one stored
+            rec.append(X2)
+            out.append(rec)
+        finally:
+            lib.mjhmc_stream_set_tma(1)
+    for a, b in zip(out[0], out[1]):
+        np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("dist_name,d", [("Gaussian", 40), ("ProductOfT", 36)])
+def test_dense_float64_job_ranges_equal_eight_particle_groups(dist_name, d):
+    """The DMMA kernel hands out ranges of 28-32 particles and packs the FLF trajectories of the particles that need
+    them in front of the L trajectories (csrc/dense.cu); clouds too small to fill the GPU are cut into ranges of 8.
+    One cloud of 60 000 particles (large ranges, range size adapting to the FLF fraction) against the same particles
+    in three launches of 20 000 (ranges of 8 only): bit-identical samples, state, dwelling times and counters."""
+    from mjhmc_b200.samplers import markov_jump_hmc as S
+    N, n = 60000, 4
+    rs = np.random.RandomState(12)
+    _, _, X0 = _dense_case(dist_name, d, N, rs)
+    V0 = rs.randn(d, N)
+    hp = dict(epsilon=0.25, beta=0.5, num_leapfrog_steps=2)
+    outs = []
+    for bounds in ([(0, N)], [(0, 20000), (20000, 40000), (40000, N)]):
+        parts, vs, dw, tot = [], [], [], np.zeros(6, dtype=np.int64)
+        for lo, hi in bounds:
+            dist, _, _ = _dense_case(dist_name, d, hi - lo, np.random.RandomState(12))
+            helpers.pin_init(dist, X0[:, lo:hi])
+            s = S.MarkovJumpHMC(distribution=dist, V=V0[:, lo:hi], seed=8, resample=False, particle_offset=lo, **hp)
+            assert s._engine.fused
+            parts.append(s.sample(n, preserve_order=True))
+            vs.append(s.state.V.copy())
+            dw.append(np.asarray(s.dwelling_times).copy())
+            tot += np.array(_counters(s, dist))
+        outs.append((np.concatenate(parts, axis=1), np.concatenate(vs, axis=1), np.concatenate(dw), tot))
+    for a, b in zip(outs[0], outs[1]):
+        np.testing.assert_array_equal(a, b)
+    assert outs[0][3][3] > 0 and outs[0][3][1] > 0          # R and F moves happened: FLF jobs were packed
+
+
 @pytest.mark.parametrize("dist_name", ["Gaussian", "ProductOfT"])
 def test_dense_float32_rows_do_not_depend_on_the_tile_packing(dist_name):
     """The tcgen05 kernel packs L jobs and the FLF jobs of uncached particles into 128-row tiles whose composition
