@@ -4,15 +4,16 @@
 //   ProductOfT                misc/distributions.py:420-433   Y = W^T X + b, E = sum_j (nu_j+1)/2 log(1 + (y_j/nu_j)^2)
 //                             (+ hand-derived autodiff of :431) G_j = (nu_j+1) y_j / (nu_j^2 + y_j^2), dEdX = W G
 //
-// Work decomposition: ONE WARP OWNS 8 PARTICLES for the whole launch.  The gradient of its 8
-// particles is a (rows x K) . (K x 8) product issued as mma.sync.m8n8k4.f64 with the matrix
-// (S, or W^T then W) as the A operand from shared memory (staged once per CTA, read by every
-// warp) and the warp's own 8 positions as the B operand from a warp-private shared tile.  The
-// accumulator layout of the MMA gives every lane a fixed set of (dimension, particle) elements:
-// the momentum of exactly those elements lives in that lane's registers across the L leapfrog
-// steps, the gradient arrives in the same registers as the MMA result, and the position goes
-// through the warp-private tile (written by its owner lane, read as the next B operand).  Warps
-// never synchronise with each other inside the sampling loop (only __syncwarp).
+// Work decomposition: A WARP RUNS 8 TRAJECTORIES AT A TIME (the N of the MMA) out of the job list of its particle
+// range (28-32 particles per range; the F.L.F trajectories of only the particles that need them, then the L
+// trajectory of every particle -- see the main loop).  The gradient of the 8 columns is a (rows x K) . (K x 8)
+// product issued as mma.sync.m8n8k4.f64 with the matrix (S, or W^T then W) as the A operand from shared memory
+// (staged once per CTA, read by every warp) and the warp's own 8 positions as the B operand from a warp-private
+// shared tile.  The accumulator layout of the MMA gives every lane a fixed set of (dimension, column) elements:
+// the momentum of exactly those elements lives in that lane's registers across the L leapfrog steps, the gradient
+// arrives in the same registers as the MMA result, and the position goes through the warp-private tile (written by
+// its owner lane, read as the next B operand).  Warps never synchronise with each other inside the sampling loop
+// (only __syncwarp).
 //
 // The particle state (X, V) stays in HBM between iterations of one launch and is re-read at the
 // start of every trajectory: at L = 10..25 the kernel does 2 d^2 L flops per 5 d S bytes

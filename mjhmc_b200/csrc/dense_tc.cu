@@ -21,13 +21,20 @@
 // fit beside the particle tile in 227 KB; three bf16 planes of ONE copy do (75 KB), at the same MMA cycle count.
 //
 // Pipeline inside a tile.  16 epilogue warps (4 threads per row: thread (m, q) owns the 8-wide core columns
-// of row m listed by tc_core() -- positions and momenta of those dims stay in its registers) and one MMA warp.
-// A product is cut into K chunks of 16 / 32 columns.  The epilogue threads write chunk c of the next A operand
-// (positions after the drift, or G for ProductOfT), fence, and arrive on bar_chunk[c]; the MMA warp waits for
-// chunk c only and issues its 12 MMAs while the epilogue threads work on chunk c+1; after the last chunk it commits
-// to bar_done.  The accumulator is double-buffered in TMEM (the Gaussian alternates D0 / D1, ProductOfT keeps Y in
-// D0 and dEdX in D1), so the MMAs of product n+1 may overwrite nothing the epilogue of product n still reads.
-// Round 1's kernel was MMA -> epilogue -> MMA strictly serial (tensor pipe 29.7 % active).
+// of row m listed by tc_core() -- positions and momenta of those dims stay in its registers), one MMA warp and three
+// helper warps.  A product is cut into K chunks of 16 / 32 columns.  The epilogue threads write chunk c of the next A
+// operand (positions after the drift, or G for ProductOfT) and arrive on bar_chunk[c]; the MMA warp waits for chunk c
+// only and issues its MMAs while the epilogue threads work on chunk c+1.  The LAST K chunk is issued per group of
+// accumulator columns (the column ranges of the epilogue's chunks) with one commit each (bar_done[c]): the epilogue of
+// the product starts on the first columns while the tensor core still works on the others.  The accumulator is
+// double-buffered in TMEM (the Gaussian alternates D0 / D1, ProductOfT keeps Y in D0 and dEdX in D1), so the MMAs of
+// product n+1 overwrite nothing the epilogue of product n still reads.  Round 1's kernel was MMA -> epilogue -> MMA
+// strictly serial (tensor pipe 29.7 % active).
+//
+// Around the trajectory.  The (dims x 128 particles) boxes of X and V of a tile live in a shared-memory stash moved
+// by TMA tensor boxes (cp.async.bulk.tensor, 32 particle columns each): loaded one tile ahead, read by the job rows,
+// overwritten with the new state and stored -- X, V and the sample record -- by the helper warps, which also draw the
+// tile's Philox uniforms and refresh the momenta of the R movers of the tile before, beside the trajectory.
 #include <cstdio>
 #include <cstring>
 #include <cuda_bf16.h>
