@@ -266,29 +266,49 @@ int mjhmc_transition(int32_t dtype, int32_t ndims, const mjhmc_hp* hp, const mjh
     return check(launch_transition(dtype, p, c, q, H_flf, (cudaStream_t)stream), "transition_kernel");
 }
 
+// Counter block housekeeping runs as two tiny kernels: a reset that needs no host synchronisation, and a fold that
+// writes the totals straight into mapped pinned host memory.  (cudaMemcpy of the block went through the device->host
+// copy engine, where it queued behind the 64 MB sample copies of the pipelined sample(): every chunk waited up to 2 ms
+// for its 2 KB of counters.)
+__global__ void counters_reset_kernel(long long* counters) {
+    const int i = threadIdx.x;
+    if (i < MJHMC_COUNTER_ROWS * MJHMC_N_COUNTERS) {
+        const int row = i / MJHMC_N_COUNTERS, c = i - row * MJHMC_N_COUNTERS;
+        counters[i] = (row < MJHMC_COUNTER_STRIPES && c == MJHMC_CNT_FAIL) ? INT64_MAX : 0;
+    }
+}
+__global__ void counters_fold_kernel(const long long* counters, long long* out) {
+    const int c = threadIdx.x;
+    if (c < MJHMC_N_COUNTERS) {
+        long long v = c == MJHMC_CNT_FAIL ? INT64_MAX : 0;
+        for (int s = 0; s < MJHMC_COUNTER_STRIPES; ++s) {
+            const long long h = counters[s * MJHMC_N_COUNTERS + c];
+            if (c == MJHMC_CNT_FAIL) v = h < v ? h : v; else v += h;
+        }
+        out[c] = v;
+        __threadfence_system();
+    }
+}
+
 int mjhmc_counters_reset(int64_t* counters, void* stream_) {
     if (!counters) return fail("NULL argument");
-    int64_t h[MJHMC_COUNTER_ROWS][MJHMC_N_COUNTERS];
-    memset(h, 0, sizeof h);
-    for (int s = 0; s < MJHMC_COUNTER_STRIPES; ++s) h[s][MJHMC_CNT_FAIL] = INT64_MAX;
-    cudaStream_t stream = (cudaStream_t)stream_;
-    if (check(cudaMemcpyAsync(counters, h, sizeof h, cudaMemcpyHostToDevice, stream), "counters_reset")) return -2;
-    return check(cudaStreamSynchronize(stream), "counters_reset");
+    static_assert(MJHMC_COUNTER_ROWS * MJHMC_N_COUNTERS <= 512, "one CTA resets the block");
+    counters_reset_kernel<<<1, 512, 0, (cudaStream_t)stream_>>>((long long*)counters);
+    return check(cudaGetLastError(), "counters_reset");
 }
 
 int mjhmc_counters_read(const int64_t* counters, int64_t* out_host, void* stream_) {
     if (!counters || !out_host) return fail("NULL argument");
-    int64_t h[MJHMC_COUNTER_STRIPES][MJHMC_N_COUNTERS];
+    static thread_local long long* mapped = nullptr;           // mapped pinned, one per host thread
+    if (!mapped && check(cudaHostAlloc((void**)&mapped, MJHMC_N_COUNTERS * sizeof(long long), cudaHostAllocMapped | cudaHostAllocPortable), "counters_read"))
+        return -2;
+    long long* dev_view = nullptr;
+    if (check(cudaHostGetDevicePointer((void**)&dev_view, mapped, 0), "counters_read")) return -2;
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (check(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, stream), "counters_read")) return -2;
+    counters_fold_kernel<<<1, 32, 0, stream>>>((const long long*)counters, dev_view);
+    if (check(cudaGetLastError(), "counters_read")) return -2;
     if (check(cudaStreamSynchronize(stream), "counters_read")) return -2;
-    for (int c = 0; c < MJHMC_N_COUNTERS; ++c) out_host[c] = 0;
-    out_host[MJHMC_CNT_FAIL] = INT64_MAX;
-    for (int s = 0; s < MJHMC_COUNTER_STRIPES; ++s)
-        for (int c = 0; c < MJHMC_N_COUNTERS; ++c) {
-            if (c == MJHMC_CNT_FAIL) { if (h[s][c] < out_host[c]) out_host[c] = h[s][c]; }
-            else out_host[c] += h[s][c];
-        }
+    for (int c = 0; c < MJHMC_N_COUNTERS; ++c) out_host[c] = mapped[c];
     return 0;
 }
 

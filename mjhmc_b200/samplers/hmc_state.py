@@ -29,12 +29,24 @@ class HMCState(object):
         st = cls.__new__(cls)
         st.parent, st.X, st.V = parent, X, V
         st.nbatch = X.shape[1]
-        st.active_idx = np.arange(st.nbatch)
-        st.cache_active = np.zeros(st.nbatch, dtype=bool) if cache_active is None else cache_active
-        st.H_cache = np.zeros(st.nbatch) if H_cache is None else H_cache
-        # an empty FLF cache is cleared on the device instead of being uploaded (the arrays above stay readable)
+        if cache_active is not None:
+            st.cache_active = cache_active
+        if H_cache is not None:
+            st.H_cache = H_cache
+        # an empty FLF cache is cleared on the device instead of being uploaded; active_idx and the empty cache arrays
+        # are made when somebody reads them (__getattr__): a megabyte-sized np.arange per assignment is a millisecond
+        # of the end-to-end step
         st._empty_cache = cache_active is None and H_cache is None
         return st
+
+    def __getattr__(self, name):
+        # only reached when normal lookup fails: the lazily built members of a from_buffers() state
+        nb = self.__dict__.get("nbatch")
+        if nb is not None and name in ("active_idx", "cache_active", "H_cache"):
+            val = np.arange(nb) if name == "active_idx" else (np.zeros(nb, dtype=bool) if name == "cache_active" else np.zeros(nb))
+            self.__dict__[name] = val
+            return val
+        raise AttributeError(name)
 
     # derived arrays (hmc_state.py:28-39, 46-53), evaluated on the device, not counted
     @property

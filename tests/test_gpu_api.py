@@ -312,6 +312,37 @@ def test_pipelined_sample_equals_single_launch():
     assert outs[0][2] == 1 and outs[1][2] == 8
 
 
+def test_state_from_pinned_buffers_equals_plain_state_assignment():
+    """bench.py's end-to-end leg hands the start state over as pinned torch tensors (HMCState.from_buffers: no host copy,
+    one async upload per array, the empty FLF cache cleared on the device): same chain as assigning a regular HMCState,
+    and the lazily built host members of such a state are there when somebody reads them."""
+    import torch
+    from mjhmc_b200.misc.distributions import RoughWell
+    from mjhmc_b200.samplers.markov_jump_hmc import MarkovJumpHMC
+    from mjhmc_b200.samplers.hmc_state import HMCState
+    rs = np.random.RandomState(3)
+    N = 1000
+    X0, V0 = rs.randn(2, N) * 3, rs.randn(2, N)
+    X1, V1 = rs.randn(2, N) * 2, rs.randn(2, N)
+    hp = dict(epsilon=0.4, beta=0.3, num_leapfrog_steps=3, seed=5, resample=False)
+    outs = []
+    for pinned in (False, True):
+        dist = helpers.pin_init(RoughWell(2, N, scale1=5, scale2=4), X0)
+        s = MarkovJumpHMC(distribution=dist, V=V0, **hp)
+        s.sample(3)
+        if pinned:
+            st = HMCState.from_buffers(s, torch.as_tensor(X1).pin_memory(), torch.as_tensor(V1).pin_memory())
+            assert st.cache_active.shape == (N,) and not st.cache_active.any() and st.H_cache.shape == (N,)
+            assert st.active_idx[-1] == N - 1
+        else:
+            st = HMCState(X1.copy(), s, V=V1.copy())
+        s.state = st
+        outs.append((s.sample(4), s.state.X.copy(), s.state.V.copy(), _counters(s, dist)))
+    for a, b in zip(outs[0][:3], outs[1][:3]):
+        np.testing.assert_array_equal(a, b)
+    assert outs[0][3] == outs[1][3]
+
+
 def test_autocorrelation_curve_and_moments_agree_statistically_with_the_oracle():
     """north_star's second check: with DIFFERENT random streams the GPU sampler and the numpy oracle must agree in
     distribution -- the fft_autocor curve (autocor.py:37-49) over the first 40 lags and the first two moments.
