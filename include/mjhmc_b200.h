@@ -225,9 +225,10 @@ int mjhmc_transition(int32_t dtype, int32_t ndims, const mjhmc_hp *hp, const mjh
 int64_t mjhmc_dense_tc_workspace_bytes(const mjhmc_dist *dist);
 int mjhmc_dense_tc_prepare(const mjhmc_dist *dist, void *stream);
 
-/* Folds the striped counter rows into host int64[MJHMC_N_COUNTERS] (synchronises the stream). */
+/* Folds the striped counter rows into host int64[MJHMC_N_COUNTERS] (a one-warp kernel writing into mapped pinned
+ * memory, then a stream synchronisation: no device->host copy engine involved). */
 int mjhmc_counters_read(const int64_t *counters, int64_t *out_host, void *stream);
-/* Resets a striped counter block (zeros, FAIL = INT64_MAX). */
+/* Resets a striped counter block (zeros, FAIL = INT64_MAX) in stream order; does not synchronise. */
 int mjhmc_counters_reset(int64_t *counters, void *stream);
 
 /* Replaces the resampling loop of ContinuousTimeHMC.sample (markov_jump_hmc.py:321-328):
