@@ -66,3 +66,21 @@ def test_objective_on_the_gpu_scores_a_faster_sampler_lower():
         assert np.isfinite(exp_coef) and np.isfinite(cos_coef) and len(t) == len(ac)
         scores.append(exp_coef)
     assert scores[0] < scores[1] and scores[0] < 0
+
+
+@pytest.mark.gpu
+def test_objective_with_its_default_cached_variance_flag_runs_without_a_cache_file(tmp_path, monkeypatch):
+    """obj_func passes use_cached_var=True like the reference (search/objective.py:40-47); the fair-initialisation
+    cache it would read is opt-in here, so without the file the call must warn and go on (the fft estimate
+    never reads the cached variance, autocor.py:107-111) instead of raising FileNotFoundError."""
+    from mjhmc_b200.misc import distributions as D
+    from mjhmc_b200.samplers.markov_jump_hmc import ControlHMC
+    from mjhmc_b200.search import objective as obj
+    np.random.seed(6)
+    dist = D.TestGaussian(ndims=2, nbatch=300)
+    from mjhmc_b200.misc import gen_mj_init
+    monkeypatch.setattr(gen_mj_init, "INIT_DIR", str(tmp_path))     # no cache file can exist here
+    cos_coef, t, exp_coef, ac, _ = obj.obj_func_helper(
+        ControlHMC, dist, False, dict(epsilon=0.8, beta=0.2, num_leapfrog_steps=3, seed=4),
+        overrides=dict(num_grad_steps=2000))
+    assert np.isfinite(exp_coef) and np.isfinite(cos_coef) and len(t) == len(ac)
